@@ -1,0 +1,130 @@
+/*
+ * sdb200.h — C ABI of the B200-native Stable Diffusion v1.4 sampling path.
+ *
+ * Drop-in boundary for the hot path of Gadersd/stable-diffusion-burn (reference @ 893fb095):
+ * these entry points are what a Rust FFI shim binds in place of the Burn tensor graph in
+ * src/backend.rs and src/model/{unet,attention,groupnorm,autoencoder}. Each function cites the
+ * reference interface it replaces. The reference-side binding is shown in INTEGRATION.md and
+ * rust/sdb200_ffi.rs.
+ *
+ * Conventions
+ *  - every call returns int: 0 = ok, non-zero = error (text via sdb_last_error); nothing
+ *    unwinds across the boundary (the reference panics / exit(1)s: src/bin/sample/main.rs:45-52).
+ *  - tensors are contiguous row-major fp32, NCHW / [n, seq, C], exactly the reference's
+ *    Tensor<B,4> / Tensor<B,3> contents. Caller owns every buffer; the library owns the context.
+ *  - host-pointer calls are synchronous on return. *_dev variants take device pointers and a
+ *    cudaStream_t (passed as void*) and are asynchronous on that stream.
+ *  - a context is bound to one CUDA device and is not re-entrant (one in-flight call per ctx).
+ *  - there is NO CPU fallback: every compute entry fails if the device path is unavailable.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdb_ctx sdb_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Replaces device selection + StableDiffusionConfig::init (src/bin/sample/main.rs:59-83,
+ * src/model/stablediffusion/mod.rs:22-39). */
+int sdb_create(int device, sdb_ctx** out);
+int sdb_destroy(sdb_ctx* ctx);
+/* ctx may be NULL: returns the last error of the calling thread (e.g. a failed sdb_create). */
+const char* sdb_last_error(sdb_ctx* ctx);
+/* "sdb200 <version> sm_100a" */
+const char* sdb_version(void);
+
+/* ---- weights -------------------------------------------------------------------------- */
+/* Tensor registry. Names are the reference's dump-dir paths (src/model/unet/load.rs:213-306,
+ * src/model/autoencoder/load.rs:16-198), e.g. "unet/input_blocks/rt1/res/conv_in/weight";
+ * Linear weights are [in,out] and conv weights OIHW as in src/model/load.rs:65-160. The extra
+ * tensor "alpha_cumulative_products" [1000] is the sampler's schedule Param
+ * (src/model/stablediffusion/mod.rs:44). */
+int sdb_tensor_count(sdb_ctx* ctx);
+int sdb_tensor_info(sdb_ctx* ctx, int index, const char** name, int64_t dims[4], int* ndim);
+/* Replaces load_tensor -> Param::from_tensor (src/model/load.rs:30-47). host: fp32, dims must match. */
+int sdb_set_tensor(sdb_ctx* ctx, const char* name, const float* host, const int64_t* dims, int ndim);
+/* Reads back the fp32 master copy (tests / checkpoint round trips). */
+int sdb_get_tensor(sdb_ctx* ctx, const char* name, float* host, int64_t count);
+/* Fills every tensor with the deterministic synthetic stream documented in
+ * stable_diffusion_burn_b200/synth.py (bit-identical to the numpy generator). */
+int sdb_init_synthetic(sdb_ctx* ctx, uint32_t seed);
+/* fp32 master arena (device pointer, bytes): one contiguous block holding every tensor, for the
+ * single init-time ncclBroadcast from rank 0. */
+int sdb_weight_arena(sdb_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* Packs the master weights into kernel layouts (fp16 K-major tiles, fused QKV/GEGLU orders).
+ * Must be called after the last sdb_set_tensor / broadcast and before any compute call. */
+int sdb_finalize_weights(sdb_ctx* ctx);
+
+/* ---- hot path, host buffers -------------------------------------------------------------- */
+/* UNet::forward (src/model/unet/mod.rs:109-142): x [n,4,H,W], one timestep for the batch,
+ * context [n,L,768] -> out [n,4,H,W]. */
+int sdb_unet_forward(sdb_ctx* ctx, const float* x, int32_t timestep, const float* context,
+                     int n, int H, int W, int L, float* out);
+/* Autoencoder::decode_latent (src/model/autoencoder/mod.rs:68-71): latent [n,4,H,W] -> img [n,3,8H,8W]. */
+int sdb_decode_latent(sdb_ctx* ctx, const float* latent, int n, int H, int W, float* img);
+/* StableDiffusion::sample_latent (src/model/stablediffusion/mod.rs:102-160), DDIM eta=0 with
+ * classifier-free guidance (forward_diffuser :162-192). context [n,L,768]; uncond [Lu,768] is
+ * broadcast over the batch. init_latent [n,4,H,W] (the reference draws it from an unseeded RNG,
+ * :115-121); if NULL an internal Philox N(0,1) stream keyed by `seed` is used. */
+int sdb_sample_latent(sdb_ctx* ctx, const float* context, int n, int L, const float* uncond, int Lu,
+                      double guidance_scale, int n_steps, const float* init_latent, uint64_t seed,
+                      int H, int W, float* latent_out);
+/* StableDiffusion::latent_to_image (src/model/stablediffusion/mod.rs:69-100): decode(latent/0.18215),
+ * (x+1)/2*255, NHWC, clamp to [0,255], truncate to u8. rgb [n,8H,8W,3]. */
+int sdb_latent_to_image(sdb_ctx* ctx, const float* latent, int n, int H, int W, uint8_t* rgb);
+/* StableDiffusion::sample_image (src/model/stablediffusion/mod.rs:51-67) = sample_latent + latent_to_image. */
+int sdb_sample_image(sdb_ctx* ctx, const float* context, int n, int L, const float* uncond, int Lu,
+                     double guidance_scale, int n_steps, const float* init_latent, uint64_t seed,
+                     int H, int W, uint8_t* rgb);
+
+/* ---- hot path, device buffers (zero-copy callers) ------------------------------------------ */
+int sdb_unet_forward_dev(sdb_ctx* ctx, const float* d_x, int32_t timestep, const float* d_context,
+                         int n, int H, int W, int L, float* d_out, void* stream);
+int sdb_decode_latent_dev(sdb_ctx* ctx, const float* d_latent, int n, int H, int W, float* d_img, void* stream);
+int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, const float* d_uncond, int Lu,
+                         double guidance_scale, int n_steps, const float* d_init_latent,
+                         int H, int W, uint8_t* d_rgb, void* stream);
+
+/* ---- configuration / instrumentation ------------------------------------------------------- */
+/* key/value knobs: "precision" = 1|2|3 tensor-core passes per product,
+ * "graphs" = 0|1 (CUDA-graph replay of the UNet step), "splitk" = 0|1. */
+int sdb_set_option(sdb_ctx* ctx, const char* key, int value);
+/* Per-kernel-class timing: when enabled, every launch is bracketed by CUDA events on the
+ * context's stream (graphs are bypassed). */
+int sdb_profile_enable(sdb_ctx* ctx, int on);
+int sdb_profile_reset(sdb_ctx* ctx);
+int sdb_profile_class_count(sdb_ctx* ctx);
+/* launches, total device milliseconds, algorithmic FLOPs and bytes of one kernel class. */
+int sdb_profile_get(sdb_ctx* ctx, int cls, const char** name, int64_t* launches, double* ms,
+                    double* flops, double* bytes);
+/* Number of kernel launches issued by this context since creation (sdb_profile_reset zeroes it). */
+int64_t sdb_launch_count(sdb_ctx* ctx);
+
+/* ---- unit-test entry points for single kernels (device pointers) ----------------------------- */
+/* C[M,N] (fp32) = A[M,K] (fp32, rounded to the operand format) x B[K,N] (fp32 [in,out]) + bias.
+ * Exercises the tcgen05 GEMM exactly as the Linear layers use it. */
+int sdb_test_linear(sdb_ctx* ctx, const float* a, const float* w, const float* bias, int M, int K, int N,
+                    int passes, float* c);
+/* conv2d NCHW fp32 in/out through the implicit-GEMM path (3x3 pad 1 stride 1|2, or 1x1). */
+int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* bias, int n, int cin, int H,
+                    int W, int cout, int ksize, int stride, int upsample, int passes, float* y);
+/* GroupNorm(32 groups)+optional SiLU, NCHW fp32 in/out. */
+int sdb_test_groupnorm(sdb_ctx* ctx, const float* x, const float* gamma, const float* beta, int n, int c,
+                       int H, int W, int silu, float* y);
+/* LayerNorm over the last dim, [rows, c]. */
+int sdb_test_layernorm(sdb_ctx* ctx, const float* x, const float* gamma, const float* beta, int rows, int c,
+                       float* y);
+/* qkv_attention (src/model/attention.rs:5-45): q [n,Nq,C], k,v [n,Nk,C], heads -> out [n,Nq,C]. */
+int sdb_test_attention(sdb_ctx* ctx, const float* q, const float* k, const float* v, int n, int Nq, int Nk,
+                       int C, int heads, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

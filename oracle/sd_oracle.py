@@ -1,0 +1,372 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY (never imported by the product path).
+
+Op-for-op torch-CPU fp32 restatement of the reference's sampling hot path
+(Gadersd/stable-diffusion-burn @ 893fb095). Every function cites the reference
+file:line it follows. The reference's arithmetic lives in third-party crates that are
+NOT vendored (burn 0.14.0 -> burn-tch 0.14.0 -> tch 0.15.0 -> libtorch), so the burn op
+semantics below are restated from their published definitions:
+  nn::Linear      y = x @ W[in,out] + b
+  nn::conv::Conv2d = at::conv2d (cross-correlation, OIHW weights, zero padding)
+  nn::LayerNorm   (x-mean)/sqrt(var_biased+eps)*gamma+beta, eps 1e-5
+  nn::Gelu        exact erf form
+  activation::softmax  exp(x-max)/sum
+  Tensor::repeat(&[..]) per-dimension tiling
+
+PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture for
+this path (its only test is the tokenizer KAT, src/tokenizer.rs:205-221) and it cannot be
+compiled or run here (no rustc/cargo, crates not vendored). This oracle is therefore
+anchored on the reference's call sites only; tests/golden/ holds outputs of THIS oracle.
+
+`dtype` may be torch.float32 (the parity target) or torch.float64 (truth for tolerance
+budgeting). `emu` optionally rounds GEMM-class operands to a tensor-core input format to
+budget the precision mode of the CUDA path (dev tool).
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_EMU = {"mode": None, "roles": "awq", "blocks": None, "cur": None}
+
+
+def set_emulation(mode, roles="awq"):
+    """None | 'fp16' | 'bf16' | 'tf32' : round GEMM-class operands (RNE), accumulate wide.
+    roles: which operand classes are rounded: 'a' activations feeding conv/linear,
+    'w' weights, 'q' attention matmul operands (q,k,p,v)."""
+    _EMU["mode"] = mode
+    _EMU["roles"] = roles
+
+
+def set_emulation_blocks(blocks):
+    """Restrict emulation to UNet blocks whose tap name is in `blocks` (None = everywhere)."""
+    _EMU["blocks"] = None if blocks is None else set(blocks)
+
+
+def _enter(block):
+    _EMU["cur"] = block
+
+
+def _q(x, role="a"):
+    m = _EMU["mode"]
+    if m is None or role not in _EMU["roles"]:
+        return x
+    if _EMU["blocks"] is not None and _EMU["cur"] not in _EMU["blocks"]:
+        return x
+    if m == "fp16":
+        return x.to(torch.float16).to(x.dtype)
+    if m == "bf16":
+        return x.to(torch.bfloat16).to(x.dtype)
+    if m == "tf32":
+        xi = x.to(torch.float32).view(torch.int32)
+        xi = (xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF
+        return xi.view(torch.float32).to(x.dtype)
+    raise ValueError(m)
+
+
+class Params:
+    """name -> tensor, names = reference dump-dir paths (src/model/*/load.rs)."""
+
+    def __init__(self, arrays: dict, dtype=torch.float32):
+        self.dtype = dtype
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in arrays.items()}
+
+    def __call__(self, name):
+        return self.t[name]
+
+    def has(self, name):
+        return name in self.t
+
+
+# ------------------------------------------------------------------ primitives
+def linear(P, name, x):
+    """burn nn::Linear: y = x W + b, W stored [in,out] (reference src/model/load.rs:65-76)."""
+    y = _q(x, "a") @ _q(P(f"{name}/weight"), "w")
+    if P.has(f"{name}/bias"):
+        y = y + P(f"{name}/bias")
+    return y
+
+
+def conv2d(P, name, x, stride=1, padding=0):
+    """burn nn::conv::Conv2d -> at::conv2d, OIHW (reference src/model/load.rs:118-160)."""
+    b = P(f"{name}/bias") if P.has(f"{name}/bias") else None
+    return F.conv2d(_q(x, "a"), _q(P(f"{name}/weight"), "w"), b, stride=stride, padding=padding)
+
+
+def silu(x):
+    """reference src/model/silu.rs:14-16: x * sigmoid(x)."""
+    return x * torch.sigmoid(x)
+
+
+def layernorm_noaffine(x, eps):
+    """reference src/model/groupnorm/mod.rs:75-82: u=x-mean; u/sqrt(mean(u*u)+eps) over last dim."""
+    u = x - x.mean(dim=-1, keepdim=True)
+    return u / ((u * u).mean(dim=-1, keepdim=True) + eps).sqrt()
+
+
+def group_norm(P, name, x, n_group=32, eps=1e-5):
+    """reference src/model/groupnorm/mod.rs:53-73: reshape [N,G,rest] -> layernorm -> *gamma[C] + beta[C]."""
+    shape = x.shape
+    n = shape[0]
+    c = shape[1]
+    y = layernorm_noaffine(x.reshape(n, n_group, -1), eps).reshape(shape)
+    aff = [1] * x.dim()
+    aff[1] = c
+    return y * P(f"{name}/weight").reshape(aff) + P(f"{name}/bias").reshape(aff)
+
+
+def nn_layer_norm(P, name, x, eps=1e-5):
+    """burn nn::LayerNorm (third-party): biased variance, eps inside sqrt, affine."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / (var + eps).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
+
+
+def gelu_erf(x):
+    """burn nn::Gelu = exact erf GELU (used at unet/mod.rs:590)."""
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def qkv_attention(q, k, v, n_head):
+    """reference src/model/attention.rs:5-45 (== src/backend.rs:88-128), mask=None."""
+    n_batch, n_qctx, n_state = q.shape
+    n_ctx = k.shape[1]
+    scale = (n_state / n_head) ** -0.25
+    n_hstate = n_state // n_head
+    q = q.reshape(n_batch, n_qctx, n_head, n_hstate).transpose(1, 2) * scale
+    k = k.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2).transpose(-1, -2) * scale
+    v = v.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2)
+    qk = _q(q, "q") @ _q(k, "q")
+    # burn softmax: exp(x - max) / sum
+    w = qk - qk.amax(dim=3, keepdim=True)
+    w = w.exp()
+    w = w / w.sum(dim=3, keepdim=True)
+    o = (_q(w, "q") @ _q(v, "q")).transpose(1, 2).flatten(2, 3)
+    return o
+
+
+def upsample_nearest2x(x):
+    """reference unet/mod.rs:390-398: reshape [n,c,h,1,w,1].repeat([1,1,1,2,1,2]).reshape."""
+    n, c, h, w = x.shape
+    return x.reshape(n, c, h, 1, w, 1).repeat(1, 1, 1, 2, 1, 2).reshape(n, c, 2 * h, 2 * w)
+
+
+# ------------------------------------------------------------------------ UNet
+def timestep_embedding(t, dim=320, max_period=10000, dtype=torch.float32):
+    """reference unet/mod.rs:19-30: freqs=exp(-ln(max_period)/half * arange(half)); [cos|sin] -> [1,dim]."""
+    half = dim // 2
+    freqs = (torch.arange(0, half, dtype=torch.int64).to(dtype) * (-math.log(max_period) / half)).exp()
+    args = torch.tensor([t], dtype=torch.int64).to(dtype) * freqs
+    return torch.cat([args.cos(), args.sin()], 0).unsqueeze(0)
+
+
+def res_block(P, name, x, emb):
+    """reference unet/mod.rs:712-734."""
+    h = group_norm(P, f"{name}/norm_in", x)
+    h = silu(h)
+    h = conv2d(P, f"{name}/conv_in", h, padding=1)
+    e = linear(P, f"{name}/lin_embed", silu(emb))
+    h = h + e.reshape(e.shape[0], e.shape[1], 1, 1)
+    h = group_norm(P, f"{name}/norm_out", h)
+    h = silu(h)
+    h = conv2d(P, f"{name}/conv_out", h, padding=1)
+    if P.has(f"{name}/skip_connection/weight"):
+        return conv2d(P, f"{name}/skip_connection", x) + h
+    return x + h
+
+
+def multi_head_attention(P, name, x, context, n_head=8):
+    """reference unet/mod.rs:641-653."""
+    xa = x if context is None else context
+    q = linear(P, f"{name}/query", x)
+    k = linear(P, f"{name}/key", xa)
+    v = linear(P, f"{name}/value", xa)
+    wv = qkv_attention(q, k, v, n_head)
+    return linear(P, f"{name}/out", wv)
+
+
+def geglu_mlp(P, name, x):
+    """reference unet/mod.rs:551-555, 578-592."""
+    p = linear(P, f"{name}/geglu/proj", x)
+    half = p.shape[-1] // 2
+    a, gate = p[..., :half], p[..., half:]
+    return linear(P, f"{name}/lin", a * gelu_erf(gate))
+
+
+def transformer_block(P, name, x, context):
+    """reference unet/mod.rs:521-527."""
+    x = x + multi_head_attention(P, f"{name}/attn1", nn_layer_norm(P, f"{name}/norm1", x), None)
+    x = x + multi_head_attention(P, f"{name}/attn2", nn_layer_norm(P, f"{name}/norm2", x), context)
+    return x + geglu_mlp(P, f"{name}/mlp", nn_layer_norm(P, f"{name}/norm3", x))
+
+
+def spatial_transformer(P, name, x, context):
+    """reference unet/mod.rs:461-481."""
+    n, c, h, w = x.shape
+    x_in = x
+    y = group_norm(P, f"{name}/norm", x)
+    y = conv2d(P, f"{name}/proj_in", y)
+    y = y.reshape(n, c, h * w).transpose(1, 2)
+    y = transformer_block(P, f"{name}/transformer", y, context)
+    y = y.transpose(1, 2).reshape(n, c, h, w)
+    return x_in + conv2d(P, f"{name}/proj_out", y)
+
+
+def _unet_block(P, name, kind, x, emb, ctx):
+    if kind == "conv":
+        return conv2d(P, name, x, padding=1)
+    if kind == "down":  # unet/mod.rs:412-427: stride 2, pad 1
+        return conv2d(P, name, x, stride=2, padding=1)
+    if kind == "r":
+        return res_block(P, name, x, emb)
+    x = res_block(P, f"{name}/res", x, emb)
+    if kind in ("rt", "rtu"):
+        x = spatial_transformer(P, f"{name}/transformer", x, ctx)
+    if kind in ("ru", "rtu"):
+        x = conv2d(P, f"{name}/upsample/conv", upsample_nearest2x(x), padding=1)
+    return x
+
+
+def unet_forward(P, x, t, context, taps=None, prefix="unet"):
+    """reference unet/mod.rs:109-142. x [n,4,H,W]; t python int (one timestep for the batch);
+    context [n,L,768]. `taps`: optional dict receiving the output of every block."""
+    from stable_diffusion_burn_b200 import topology as T
+    x = x.to(P.dtype)
+    context = context.to(P.dtype)
+    _enter("emb")
+    t_emb = timestep_embedding(int(t), 320, 10000, P.dtype)
+    emb = linear(P, f"{prefix}/lin1_time_embed", t_emb)
+    emb = silu(emb)
+    emb = linear(P, f"{prefix}/lin2_time_embed", emb)
+    if taps is not None:
+        taps["emb"] = emb
+    saved = []
+    for f, kind, _, _ in T.UNET_INPUT_BLOCKS:
+        _enter(f"input_blocks/{f}")
+        x = _unet_block(P, f"{prefix}/input_blocks/{f}", kind, x, emb, context)
+        saved.append(x)
+        if taps is not None:
+            taps[f"input_blocks/{f}"] = x
+    m = f"{prefix}/middle_block"
+    _enter("middle_block")
+    x = res_block(P, f"{m}/res1", x, emb)
+    x = spatial_transformer(P, f"{m}/transformer", x, context)
+    x = res_block(P, f"{m}/res2", x, emb)
+    if taps is not None:
+        taps["middle_block"] = x
+    for f, kind, _, _ in T.UNET_OUTPUT_BLOCKS:
+        x = torch.cat([x, saved.pop()], 1)
+        _enter(f"output_blocks/{f}")
+        x = _unet_block(P, f"{prefix}/output_blocks/{f}", kind, x, emb, context)
+        if taps is not None:
+            taps[f"output_blocks/{f}"] = x
+    _enter("out")
+    x = group_norm(P, f"{prefix}/norm_out", x)
+    x = silu(x)
+    return conv2d(P, f"{prefix}/conv_out", x, padding=1)
+
+
+# ------------------------------------------------------------------ VAE decoder
+def resnet_block(P, name, x):
+    """reference autoencoder/mod.rs:513-528."""
+    h = conv2d(P, f"{name}/conv1", silu(group_norm(P, f"{name}/norm1", x)), padding=1)
+    h = conv2d(P, f"{name}/conv2", silu(group_norm(P, f"{name}/norm2", h)), padding=1)
+    if P.has(f"{name}/nin_shortcut/weight"):
+        return conv2d(P, f"{name}/nin_shortcut", x) + h
+    return x + h
+
+
+def conv_self_attention_block(P, name, x):
+    """reference autoencoder/mod.rs:562-608 (1 head, d = C)."""
+    n, c, hh, ww = x.shape
+    h = group_norm(P, f"{name}/norm", x)
+    q = conv2d(P, f"{name}/q", h).reshape(n, c, hh * ww).transpose(1, 2)
+    k = conv2d(P, f"{name}/k", h).reshape(n, c, hh * ww).transpose(1, 2)
+    v = conv2d(P, f"{name}/v", h).reshape(n, c, hh * ww).transpose(1, 2)
+    wv = qkv_attention(q, k, v, 1).transpose(1, 2).reshape(n, c, hh, ww)
+    return x + conv2d(P, f"{name}/proj_out", wv)
+
+
+def decode_latent(P, latent, taps=None, prefix="autoencoder"):
+    """reference autoencoder/mod.rs:68-71 + Decoder::forward :204-217 + DecoderBlock :307-324 + Mid :456-463."""
+    from stable_diffusion_burn_b200 import topology as T
+    x = conv2d(P, f"{prefix}/post_quant_conv", latent.to(P.dtype))
+    d = f"{prefix}/decoder"
+    x = conv2d(P, f"{d}/conv_in", x, padding=1)
+    x = resnet_block(P, f"{d}/mid/block_1", x)
+    x = conv_self_attention_block(P, f"{d}/mid/attn", x)
+    x = resnet_block(P, f"{d}/mid/block_2", x)
+    if taps is not None:
+        taps["mid"] = x
+    nb = len(T.VAE_DECODER_BLOCKS)
+    for i in range(nb):
+        b = f"{d}/blocks/{i}"
+        x = resnet_block(P, f"{b}/res1", x)
+        x = resnet_block(P, f"{b}/res2", x)
+        x = resnet_block(P, f"{b}/res3", x)
+        if i != nb - 1:
+            x = conv2d(P, f"{b}/upsampler", upsample_nearest2x(x), padding=1)
+        if taps is not None:
+            taps[f"blocks/{i}"] = x
+    return conv2d(P, f"{d}/conv_out", silu(group_norm(P, f"{d}/norm_out", x)), padding=1)
+
+
+# -------------------------------------------------------------------- pipeline
+def forward_diffuser(P, latent, t, context, uncond, scale):
+    """reference stablediffusion/mod.rs:162-192. `uncond` [Lu,768] is broadcast over the batch
+    (the evident intent of `.unsqueeze().repeat(&[0, n_batch])`)."""
+    n = latent.shape[0]
+    u_ctx = uncond.unsqueeze(0).repeat(n, 1, 1)
+    u = unet_forward(P, latent, t, u_ctx)
+    c = unet_forward(P, latent, t, context)
+    return u + (c - u) * scale
+
+
+def ddim_timesteps(n_steps, n_train=1000):
+    """reference stablediffusion/mod.rs:111,123: (0..1000).rev().step_by(1000 / n_steps)."""
+    step = n_train // n_steps
+    return list(range(n_train - 1, -1, -step)), step
+
+
+def sample_latent(P, context, uncond, scale, n_steps, init_latent, taps=None):
+    """reference stablediffusion/mod.rs:102-160 (sigma = 0; the initial N(0,1) latent is an input
+    because the reference's RNG is unseeded). Alphas are read as f32, widened to f64 (`.to_f64()`),
+    and the scalar coefficients are applied as tensor-by-scalar ops."""
+    alphas = P("alpha_cumulative_products").to(torch.float32)
+    ts, step = ddim_timesteps(n_steps)
+    latent = init_latent.to(P.dtype)
+    sigma = 0.0
+    for i, t in enumerate(ts):
+        a_t = float(alphas[t])
+        a_prev = float(alphas[t - step]) if t >= step else 1.0
+        sqrt_noise = math.sqrt(1.0 - a_t)
+        pred = forward_diffuser(P, latent, t, context, uncond, scale)
+        predx0 = (latent - pred * sqrt_noise) / math.sqrt(a_t)
+        dir_latent = pred * math.sqrt(1.0 - a_prev - sigma * sigma)
+        latent = predx0 * math.sqrt(a_prev) + dir_latent  # + gen_noise()*sigma, sigma == 0
+        if taps is not None:
+            taps[f"step{i}/pred"] = pred
+            taps[f"step{i}/latent"] = latent
+    return latent
+
+
+def latent_to_image_f32(P, latent):
+    """reference stablediffusion/mod.rs:69-84 up to (not including) the u8 cast: [n,H,W,3] floats."""
+    img = decode_latent(P, latent * (1.0 / 0.18215))
+    img = (img + 1.0) / 2.0
+    return img.permute(0, 2, 3, 1) * 255.0
+
+
+def to_u8(img_f):
+    """reference stablediffusion/mod.rs:94-97: v.to_f64().min(255.0).max(0.0) as u8 (truncation; NaN -> 255->... `as u8` of NaN is 0 after min/max keeps 255: f64::min(NaN,255)=255)."""
+    a = img_f.detach().to(torch.float64).numpy()
+    a = np.where(np.isnan(a), 255.0, a)
+    a = np.maximum(np.minimum(a, 255.0), 0.0)
+    return a.astype(np.uint8)  # truncation toward zero
+
+
+def sample_image(P, context, uncond, scale, n_steps, init_latent):
+    """reference stablediffusion/mod.rs:51-67 -> list of n HWC u8 arrays flattened like Vec<Vec<u8>>."""
+    lat = sample_latent(P, context, uncond, scale, n_steps, init_latent)
+    return to_u8(latent_to_image_f32(P, lat))

@@ -1,0 +1,397 @@
+// api.cu — extern "C" boundary (include/sdb200.h). No exception crosses it.
+#include "../../include/sdb200.h"
+
+#include <cstring>
+#include <mutex>
+
+#include "model.cuh"
+#include "runtime.cuh"
+
+using namespace sdb;
+
+struct sdb_ctx {
+  Ctx c;
+};
+
+static thread_local std::string g_err;
+
+#define API_BEGIN(ctxp)                      \
+  if (!(ctxp)) {                             \
+    g_err = "null context";                  \
+    return 1;                                \
+  }                                          \
+  Ctx& c = (ctxp)->c;                        \
+  try {                                      \
+    SDB_CUDA(cudaSetDevice(c.device));
+
+#define API_END                              \
+  }                                          \
+  catch (const std::exception& e) {          \
+    c.err = e.what();                        \
+    g_err = c.err;                           \
+    return 1;                                \
+  }                                          \
+  return 0;
+
+extern "C" {
+
+const char* sdb_version(void) { return "sdb200 0.1.0 sm_100a"; }
+
+int sdb_create(int device, sdb_ctx** out) {
+  if (!out) {
+    g_err = "null out pointer";
+    return 1;
+  }
+  *out = nullptr;
+  sdb_ctx* h = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                  "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) throw Error("device index out of range");
+    SDB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SDB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw Error(std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                  "; kernels are built for sm_100a only");
+    h = new sdb_ctx();
+    h->c.device = device;
+    SDB_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    model_create(h->c);
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    delete h;
+    return 1;
+  }
+}
+
+int sdb_destroy(sdb_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->c.device);
+  cudaDeviceSynchronize();
+  model_destroy(ctx->c);
+  ctx->c.master.destroy();
+  ctx->c.packed.destroy();
+  ctx->c.work.destroy();
+  if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return 0;
+}
+
+const char* sdb_last_error(sdb_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_err.c_str(); }
+
+// ------------------------------------------------------------------------------ weights
+int sdb_tensor_count(sdb_ctx* ctx) { return ctx ? (int)ctx->c.tensors.size() : -1; }
+
+int sdb_tensor_info(sdb_ctx* ctx, int index, const char** name, int64_t dims[4], int* ndim) {
+  API_BEGIN(ctx)
+  SDB_CHECK(index >= 0 && index < (int)c.tensors.size(), "tensor index");
+  const TensorInfo& t = c.tensors[index];
+  if (name) *name = t.name.c_str();
+  if (dims)
+    for (int i = 0; i < 4; ++i) dims[i] = t.dims[i];
+  if (ndim) *ndim = t.ndim;
+  API_END
+}
+
+int sdb_set_tensor(sdb_ctx* ctx, const char* name, const float* host, const int64_t* dims, int ndim) {
+  API_BEGIN(ctx)
+  SDB_CHECK(name && host && dims, "null argument");
+  const TensorInfo& t = c.info(name);
+  SDB_CHECK(ndim == t.ndim, std::string("rank mismatch for ") + name);
+  for (int i = 0; i < ndim; ++i) SDB_CHECK(dims[i] == t.dims[i], std::string("shape mismatch for ") + name);
+  SDB_CUDA(cudaMemcpyAsync(c.master_ptr(name), host, t.count * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  c.finalized = false;
+  API_END
+}
+
+int sdb_get_tensor(sdb_ctx* ctx, const char* name, float* host, int64_t count) {
+  API_BEGIN(ctx)
+  const TensorInfo& t = c.info(name);
+  SDB_CHECK(count == t.count, "element count mismatch");
+  SDB_CUDA(cudaMemcpyAsync(host, c.master_ptr(name), t.count * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_init_synthetic(sdb_ctx* ctx, uint32_t seed) {
+  API_BEGIN(ctx)
+  model_init_synthetic(c, seed);
+  c.finalized = false;
+  API_END
+}
+
+int sdb_weight_arena(sdb_ctx* ctx, void** dev_ptr, size_t* bytes) {
+  API_BEGIN(ctx)
+  if (dev_ptr) *dev_ptr = c.master.base;
+  if (bytes) *bytes = c.master.off;
+  API_END
+}
+
+int sdb_finalize_weights(sdb_ctx* ctx) {
+  API_BEGIN(ctx)
+  model_finalize(c);
+  c.finalized = true;
+  API_END
+}
+
+// ------------------------------------------------------------------------------ hot path
+static void need_final(Ctx& c) { SDB_CHECK(c.finalized, "call sdb_finalize_weights first"); }
+
+int sdb_unet_forward(sdb_ctx* ctx, const float* x, int32_t timestep, const float* context, int n, int H, int W, int L,
+                     float* out) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_unet_forward_host(c, x, timestep, context, n, H, W, L, out);
+  API_END
+}
+
+int sdb_unet_forward_dev(sdb_ctx* ctx, const float* d_x, int32_t timestep, const float* d_context, int n, int H, int W,
+                         int L, float* d_out, void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_unet_forward_dev(c, d_x, timestep, d_context, n, H, W, L, d_out, (cudaStream_t)stream);
+  API_END
+}
+
+int sdb_decode_latent(sdb_ctx* ctx, const float* latent, int n, int H, int W, float* img) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_decode_host(c, latent, n, H, W, img);
+  API_END
+}
+
+int sdb_decode_latent_dev(sdb_ctx* ctx, const float* d_latent, int n, int H, int W, float* d_img, void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_decode_dev(c, d_latent, n, H, W, d_img, (cudaStream_t)stream);
+  API_END
+}
+
+int sdb_sample_latent(sdb_ctx* ctx, const float* context, int n, int L, const float* uncond, int Lu,
+                      double guidance_scale, int n_steps, const float* init_latent, uint64_t seed, int H, int W,
+                      float* latent_out) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_sample_host(c, context, n, L, uncond, Lu, guidance_scale, n_steps, init_latent, seed, H, W, latent_out, nullptr);
+  API_END
+}
+
+int sdb_latent_to_image(sdb_ctx* ctx, const float* latent, int n, int H, int W, uint8_t* rgb) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_latent_to_image_host(c, latent, n, H, W, rgb);
+  API_END
+}
+
+int sdb_sample_image(sdb_ctx* ctx, const float* context, int n, int L, const float* uncond, int Lu, double guidance_scale,
+                     int n_steps, const float* init_latent, uint64_t seed, int H, int W, uint8_t* rgb) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_sample_host(c, context, n, L, uncond, Lu, guidance_scale, n_steps, init_latent, seed, H, W, nullptr, rgb);
+  API_END
+}
+
+int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, const float* d_uncond, int Lu,
+                         double guidance_scale, int n_steps, const float* d_init_latent, int H, int W, uint8_t* d_rgb,
+                         void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_sample_dev(c, d_context, n, L, d_uncond, Lu, guidance_scale, n_steps, d_init_latent, H, W, nullptr, d_rgb,
+                   (cudaStream_t)stream);
+  API_END
+}
+
+// ------------------------------------------------------------------------------ options / profiling
+int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
+  API_BEGIN(ctx)
+  const std::string k = key ? key : "";
+  if (k == "precision")
+    c.opt_precision = value;
+  else if (k == "graphs")
+    c.opt_graphs = value;
+  else if (k == "splitk")
+    c.opt_splitk = value;
+  else
+    throw Error("unknown option: " + k);
+  model_invalidate_graphs(c);
+  API_END
+}
+
+int sdb_profile_enable(sdb_ctx* ctx, int on) {
+  API_BEGIN(ctx)
+  profile_collect(c);
+  c.profiling = on != 0;
+  API_END
+}
+int sdb_profile_reset(sdb_ctx* ctx) {
+  API_BEGIN(ctx)
+  profile_collect(c);
+  c.launches = 0;
+  for (int i = 0; i < KC_COUNT; ++i) c.cls_ms[i] = c.cls_flops[i] = c.cls_bytes[i] = 0, c.cls_launches[i] = 0;
+  API_END
+}
+int sdb_profile_class_count(sdb_ctx*) { return KC_COUNT; }
+int sdb_profile_get(sdb_ctx* ctx, int cls, const char** name, int64_t* launches, double* ms, double* flops, double* bytes) {
+  API_BEGIN(ctx)
+  SDB_CHECK(cls >= 0 && cls < KC_COUNT, "class index");
+  profile_collect(c);
+  if (name) *name = kernel_class_name(cls);
+  if (launches) *launches = c.cls_launches[cls];
+  if (ms) *ms = c.cls_ms[cls];
+  if (flops) *flops = c.cls_flops[cls];
+  if (bytes) *bytes = c.cls_bytes[cls];
+  API_END
+}
+int64_t sdb_launch_count(sdb_ctx* ctx) { return ctx ? ctx->c.launches : -1; }
+
+// ------------------------------------------------------------------------------ single-kernel test entries
+// (host pointers; each call stages through the context's work arena)
+int sdb_test_linear(sdb_ctx* ctx, const float* a, const float* w, const float* bias, int M, int K, int N, int passes,
+                    float* out) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  float* d_a = c.work.get<float>((size_t)M * K);
+  float* d_w = c.work.get<float>((size_t)K * N);
+  float* d_b = bias ? c.work.get<float>(N) : nullptr;
+  float* d_c = c.work.get<float>((size_t)M * N);
+  SDB_CUDA(cudaMemcpyAsync(d_a, a, sizeof(float) * M * K, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_w, w, sizeof(float) * K * N, cudaMemcpyHostToDevice, c.stream));
+  if (bias) SDB_CUDA(cudaMemcpyAsync(d_b, bias, sizeof(float) * N, cudaMemcpyHostToDevice, c.stream));
+  ActOp A;
+  A.p.hi = c.work.get<__half>((size_t)M * K);
+  A.p.lo = c.work.get<__half>((size_t)M * K);
+  A.W = M, A.C = K;
+  WeightOp Wp;
+  Wp.p.hi = c.work.get<__half>((size_t)N * K);
+  Wp.p.lo = c.work.get<__half>((size_t)N * K);
+  Wp.N = N, Wp.K = K;
+  convert_f16_launch(d_a, (long long)M * K, A.p, c.stream);
+  pack_linear_launch(d_w, K, N, Wp.p, 0, c.stream);
+  Epilogue ep;
+  ep.out_f32 = d_c;
+  ep.bias = d_b;
+  run_gemm(c, G_LINEAR, A, nullptr, Wp, passes, ep);
+  SDB_CUDA(cudaMemcpyAsync(out, d_c, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* bias, int n, int cin, int H, int W,
+                    int cout, int ksize, int stride, int upsample, int passes, float* y) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  SDB_CHECK(ksize == 1 || ksize == 3, "ksize");
+  SDB_CHECK(stride == 1 || (stride == 2 && ksize == 3 && !upsample), "stride");
+  const int Hin = H, Win = W;
+  const int Ho = upsample ? 2 * H : (stride == 2 ? H / 2 : H), Wo = upsample ? 2 * W : (stride == 2 ? W / 2 : W);
+  const size_t xin = (size_t)n * cin * Hin * Win, yout = (size_t)n * cout * Ho * Wo;
+  float* d_x = c.work.get<float>(xin);
+  float* d_xh = c.work.get<float>(xin);
+  float* d_w = c.work.get<float>((size_t)cout * cin * ksize * ksize);
+  float* d_b = bias ? c.work.get<float>(cout) : nullptr;
+  float* d_yh = c.work.get<float>(yout);
+  float* d_y = c.work.get<float>(yout);
+  SDB_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * xin, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_w, w, sizeof(float) * cout * cin * ksize * ksize, cudaMemcpyHostToDevice, c.stream));
+  if (bias) SDB_CUDA(cudaMemcpyAsync(d_b, bias, sizeof(float) * cout, cudaMemcpyHostToDevice, c.stream));
+  nchw_to_nhwc_launch(d_x, n, cin, Hin, Win, d_xh, c.stream);
+  ActOp A;
+  A.n = n, A.C = cin;
+  WeightOp Wp;
+  Wp.N = cout;
+  int kind, mode = 0;
+  if (ksize == 1) {
+    kind = G_CONV1, A.H = Hin, A.W = Win;
+    Wp.K = cin;
+  } else if (stride == 2) {
+    kind = G_CONV3_S2, mode = PREP_PHASE2, A.P = 4, A.H = Hin / 2, A.W = Win / 2;
+    Wp.K = 9 * cin;
+  } else if (upsample == 1) {
+    kind = G_CONV3_UP2, A.H = Hin, A.W = Win;
+    Wp.K = 4 * cin;
+  } else if (upsample == 2) {
+    kind = G_CONV3, mode = PREP_UP2, A.H = 2 * Hin, A.W = 2 * Win;
+    Wp.K = 9 * cin;
+  } else {
+    kind = G_CONV3, A.H = Hin, A.W = Win;
+    Wp.K = 9 * cin;
+  }
+  const size_t a_elems = (size_t)n * A.P * A.H * A.W * cin;
+  A.p.hi = c.work.get<__half>(a_elems);
+  A.p.lo = c.work.get<__half>(a_elems);
+  const size_t w_elems = (size_t)cout * Wp.K * (kind == G_CONV3_UP2 ? 4 : 1);
+  Wp.p.hi = c.work.get<__half>(w_elems);
+  Wp.p.lo = c.work.get<__half>(w_elems);
+  prep_operand_launch(d_xh, cin, nullptr, 0, n, Hin, Win, mode, nullptr, nullptr, nullptr, 0.f, A.p, c.stream);
+  if (kind == G_CONV3_UP2)
+    pack_conv_up2_launch(d_w, cout, cin, Wp.p, c.stream);
+  else
+    pack_conv_launch(d_w, cout, cin, ksize, Wp.p, c.stream);
+  Epilogue ep;
+  ep.out_f32 = d_yh;
+  ep.bias = d_b;
+  run_gemm(c, kind, A, nullptr, Wp, passes, ep);
+  nhwc_to_nchw_launch(d_yh, n, cout, Ho, Wo, d_y, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * yout, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_groupnorm(sdb_ctx* ctx, const float* x, const float* gamma, const float* beta, int n, int ch, int H, int W,
+                       int silu, float* y) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  const size_t cnt = (size_t)n * ch * H * W;
+  float* d_x = c.work.get<float>(cnt);
+  float* d_xh = c.work.get<float>(cnt);
+  float* d_yh = c.work.get<float>(cnt);
+  float* d_y = c.work.get<float>(cnt);
+  float* d_g = c.work.get<float>(ch);
+  float* d_b = c.work.get<float>(ch);
+  double* d_s = c.work.get<double>((size_t)n * 64);
+  SDB_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_g, gamma, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_b, beta, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemsetAsync(d_s, 0, sizeof(double) * n * 64, c.stream));
+  nchw_to_nhwc_launch(d_x, n, ch, H, W, d_xh, c.stream);
+  gn_stats_launch(d_xh, ch, nullptr, 0, n, H * W, d_s, c.stream);
+  gn_apply_f32_launch(d_xh, ch, n, H * W, silu, d_s, d_g, d_b, 1e-5f, d_yh, c.stream);
+  nhwc_to_nchw_launch(d_yh, n, ch, H, W, d_y, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * cnt, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_layernorm(sdb_ctx* ctx, const float* x, const float* gamma, const float* beta, int rows, int ch, float* y) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  const size_t cnt = (size_t)rows * ch;
+  float* d_x = c.work.get<float>(cnt);
+  float* d_y = c.work.get<float>(cnt);
+  float* d_g = c.work.get<float>(ch);
+  float* d_b = c.work.get<float>(ch);
+  SDB_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_g, gamma, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_b, beta, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
+  layernorm_launch(d_x, rows, ch, d_g, d_b, 1e-5f, Half2Ptr{}, d_y, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * cnt, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_attention(sdb_ctx* ctx, const float* q, const float* k, const float* v, int n, int Nq, int Nk, int C,
+                       int heads, float* out) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  model_test_attention(c, q, k, v, n, Nq, Nk, C, heads, out);
+  API_END
+}
+
+}  // extern "C"

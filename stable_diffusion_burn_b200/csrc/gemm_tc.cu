@@ -1,0 +1,370 @@
+// gemm_tc.cu — tcgen05 implicit-GEMM for conv3x3 / conv1x1 / Linear on sm_100a.
+//
+// Replaces burn nn::conv::Conv2d / nn::Linear on the reference hot path
+// (call sites: src/model/unet/mod.rs:716,726,729 ResBlock convs; :468,479 proj_in/out;
+//  :645-651 q/k/v/out; :580,553 GEGLU/ff; src/model/autoencoder/mod.rs:513-528, 567-606).
+//
+// One CTA = one 128 x BN output tile (x one K split). Warp roles:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 5-D activation boxes + 2-D weight boxes)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (fp16 x fp16 -> fp32 in TMEM)
+//   warps 2-5: epilogue (tcgen05.ld -> bias / time-embedding row / residual / GEGLU -> global)
+// Multi-pass products (PASSES = 2, 3) add the low-order fp16 halves of the operands
+// (A_lo*B_hi, A_hi*B_lo) into the same accumulator for fp32-class accuracy.
+#include "gemm_tc.cuh"
+
+namespace sdb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // fp16 elements per k chunk = 128 bytes = one swizzle row
+static constexpr int A_TILE_BYTES = BM * BK * 2;
+
+template <int BN, int PASSES>
+struct StageLayout {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int A_TILES = PASSES >= 2 ? 2 : 1;
+  static constexpr int B_TILES = PASSES >= 3 ? 2 : 1;
+  static constexpr int BYTES = A_TILES * A_TILE_BYTES + B_TILES * B_TILE_BYTES;
+};
+
+template <int BN, int PASSES, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  using L = StageLayout<BN, PASSES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int mt = blockIdx.x;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th = mt % p.tiles_h;
+  const int tn = mt / p.tiles_h;
+  const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+  const int col0 = blockIdx.y * BN;
+
+  const int total_iters = p.num_taps * p.kc;
+  const int per_split = (total_iters + p.split_k - 1) / p.split_k;
+  const int it_begin = blockIdx.z * per_split;
+  const int it_end = min(total_iters, it_begin + per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0][0]);
+    tma_prefetch_desc(&maps.b[0]);
+    if (p.kc0 < p.kc) tma_prefetch_desc(&maps.a[1][0]);
+  }
+  constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // power of two >= BN
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], L::BYTES);
+        uint8_t* st = smem + s * L::BYTES;
+        const int tap = it / p.kc;
+        const int cc = it - tap * p.kc;
+        const int src = cc >= p.kc0 ? 1 : 0;
+        const int c0 = (cc - (src ? p.kc0 : 0)) * BK;
+        const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
+        tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
+        if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
+        uint8_t* sb = st + L::A_TILES * A_TILE_BYTES;
+        tma_load_2d(sb, &maps.b[0], &full_bar[s], it * BK, col0);
+        if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &maps.b[1], &full_bar[s], it * BK, col0);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = it_begin; it < it_end; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * L::BYTES);
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = a_hi + L::A_TILES * A_TILE_BYTES;
+        const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes inside the 128B swizzle row
+          const uint64_t da = make_sdesc_sw128(a_hi + koff);
+          const uint64_t db = make_sdesc_sw128(b_hi + koff);
+          umma_f16(tmem_base, da, db, idesc, (it > it_begin || k > 0) ? 1u : 0u);
+          if (PASSES >= 2) umma_f16(tmem_base, make_sdesc_sw128(a_lo + koff), db, idesc, 1u);
+          if (PASSES >= 3) umma_f16(tmem_base, da, make_sdesc_sw128(b_lo + koff), idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);                      // frees the smem slot when these MMAs retire
+        if (it == it_end - 1) umma_commit(accum_bar);    // accumulator complete
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;        // accumulator row
+    const int pw = w0 + r % p.TW;
+    const int phh = h0 + (r / p.TW) % p.TH;
+    const int pn = n0 + r / (p.TW * p.TH);
+    const bool row_ok = (pw < p.W) && (phh < p.H) && (pn < p.nimg);
+    const long long m = ((long long)pn * p.OH + (long long)phh * p.os + p.oa) * p.OW + (long long)pw * p.os + p.ob;
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+
+    if (p.split_k > 1) {
+      // raw partial sums -> workspace [split][M][N]
+      const long long Mtot = (long long)p.nimg * p.OH * p.OW;
+      float* wsrow = p.ws + ((long long)blockIdx.z * Mtot + m) * p.N + col0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        if (row_ok && col0 + c < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(wsrow + c + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
+      }
+    } else if (p.geglu) {
+      // tile columns [0,BN/2) = x, [BN/2,BN) = gate; output columns blockIdx.y*BN/2 + [0,BN/2)
+      constexpr int HB = BN / 2;
+      const int ocol0 = blockIdx.y * HB;
+#pragma unroll 1
+      for (int c = 0; c < HB; c += 32) {
+        uint32_t vx[32], vg[32];
+        tmem_ld32(trow + c, vx);
+        tmem_ld32(trow + HB + c, vg);
+        tmem_ld_wait();
+        if (row_ok && col0 + c < p.N) {
+          __half* o = p.out_f16 + m * p.ldc16 + ocol0 + c;
+          __half* ol = p.out_f16_lo ? p.out_f16_lo + m * p.ldc16 + ocol0 + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0 = __uint_as_float(vx[j]) + p.bias[col0 + c + j];
+            float x1 = __uint_as_float(vx[j + 1]) + p.bias[col0 + c + j + 1];
+            float g0 = __uint_as_float(vg[j]) + p.bias[col0 + HB + c + j];
+            float g1 = __uint_as_float(vg[j + 1]) + p.bias[col0 + HB + c + j + 1];
+            float y0 = x0 * gelu_erf_f(g0), y1 = x1 * gelu_erf_f(g1);
+            __half2 h = __floats2half2_rn(y0, y1);
+            *reinterpret_cast<__half2*>(o + j) = h;
+            if (ol) {
+              float2 hf = __half22float2(h);
+              *reinterpret_cast<__half2*>(ol + j) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c, v);
+        tmem_ld_wait();
+        if (row_ok && col0 + c < p.N) {
+          const int col = col0 + c;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+            }
+          }
+          if (p.rowbias) {
+            const float* rb = p.rowbias + (long long)pn * p.N + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(rb + j);
+              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+            }
+          }
+          if (p.residual) {
+            const float* rs = p.residual + m * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(rs + j);
+              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+            }
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + m * p.ldc + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+          if (p.out_f16) {
+            __half* o = p.out_f16 + m * p.ldc16 + col;
+            __half* ol = p.out_f16_lo ? p.out_f16_lo + m * p.ldc16 + col : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              __half2 h = __floats2half2_rn(f[j], f[j + 1]);
+              *reinterpret_cast<__half2*>(o + j) = h;
+              if (ol) {
+                float2 hf = __half22float2(h);
+                *reinterpret_cast<__half2*>(ol + j) = __floats2half2_rn(f[j] - hf.x, f[j + 1] - hf.y);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ split-K reduction + epilogue
+__global__ void splitk_reduce_kernel(const GemmParams p, long long Mtot) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of the output
+  const int n4 = p.N / 4;
+  if (idx >= Mtot * n4) return;
+  const long long m = idx / n4;
+  const int col = int(idx - m * n4) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < p.split_k; ++z) {  // fixed order: deterministic
+    float4 v = *reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + m) * p.N + col);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  if (p.bias) {
+    float4 b = *reinterpret_cast<const float4*>(p.bias + col);
+    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+  }
+  if (p.rowbias) {
+    const long long pn = m / ((long long)p.OH * p.OW);
+    float4 b = *reinterpret_cast<const float4*>(p.rowbias + pn * p.N + col);
+    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+  }
+  if (p.residual) {
+    float4 b = *reinterpret_cast<const float4*>(p.residual + m * p.ldc + col);
+    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+  }
+  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ldc + col) = acc;
+  if (p.out_f16) {
+    __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+    __half2* o = reinterpret_cast<__half2*>(p.out_f16 + m * p.ldc16 + col);
+    o[0] = h0, o[1] = h1;
+    if (p.out_f16_lo) {
+      float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2* ol = reinterpret_cast<__half2*>(p.out_f16_lo + m * p.ldc16 + col);
+      ol[0] = __floats2half2_rn(acc.x - f0.x, acc.y - f0.y);
+      ol[1] = __floats2half2_rn(acc.z - f1.x, acc.w - f1.y);
+    }
+  }
+}
+
+void splitk_reduce_launch(const GemmParams& p, cudaStream_t stream) {
+  const long long Mtot = (long long)p.nimg * p.OH * p.OW;
+  const long long work = Mtot * (p.N / 4);
+  const int threads = 256;
+  const long long blocks = (work + threads - 1) / threads;
+  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, Mtot);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ launcher
+template <int BN, int PASSES>
+constexpr int pick_stages() {
+  // as many stages as fit in ~200 KB, capped at 8
+  constexpr int per = StageLayout<BN, PASSES>::BYTES;
+  constexpr int n = (200 * 1024) / per;
+  return n > 8 ? 8 : n;
+}
+template <int BN, int PASSES>
+constexpr int pick_stages_half() {
+  // configuration that lets two CTAs share one SM (<= ~110 KB each)
+  constexpr int per = StageLayout<BN, PASSES>::BYTES;
+  constexpr int n = (104 * 1024) / per;
+  return n > 4 ? 4 : (n < 2 ? 2 : n);
+}
+
+template <int BN, int PASSES, int STAGES>
+static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * StageLayout<BN, PASSES>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
+  gemm_tc_kernel<BN, PASSES, STAGES><<<grid, 192, smem, stream>>>(maps, p);
+  SDB_CUDA(cudaGetLastError());
+}
+
+template <int BN, int PASSES>
+static void launch_bn(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+  const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * p.split_k;
+  // many short tiles: two co-resident CTAs per SM overlap one tile's epilogue with the other's mainloop
+  if (ctas >= 2 * 148 && pick_stages_half<BN, PASSES>() * StageLayout<BN, PASSES>::BYTES <= 104 * 1024)
+    launch_inst<BN, PASSES, pick_stages_half<BN, PASSES>()>(maps, p, stream);
+  else
+    launch_inst<BN, PASSES, pick_stages<BN, PASSES>()>(maps, p, stream);
+}
+
+void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream) {
+  SDB_CHECK(p.TN * p.TH * p.TW == BM, "M tile must cover 128 rows");
+  SDB_CHECK(p.N % 32 == 0, "N must be a multiple of 32");
+#define SDB_DISPATCH(bn)                                             \
+  case bn:                                                           \
+    if (passes == 1) launch_bn<bn, 1>(maps, p, stream);              \
+    else if (passes == 2) launch_bn<bn, 2>(maps, p, stream);         \
+    else launch_bn<bn, 3>(maps, p, stream);                          \
+    break;
+  switch (BN) {
+    SDB_DISPATCH(64)
+    SDB_DISPATCH(128)
+    SDB_DISPATCH(160)
+    SDB_DISPATCH(256)
+    default:
+      throw Error("unsupported BN");
+  }
+#undef SDB_DISPATCH
+}
+
+}  // namespace sdb

@@ -1,0 +1,49 @@
+// gemm_tc.cuh — descriptor of one tcgen05 implicit-GEMM launch (conv3x3 / conv1x1 / Linear).
+#pragma once
+#include "common.cuh"
+
+namespace sdb {
+
+// A operand = fp16 activation tensor viewed as 5-D [n][phase][h][w][c] (c innermost), loaded by TMA
+// boxes {64 c, TW, TH, 1, TN} at tap-shifted coordinates (zero fill outside = conv padding).
+// B operand = packed fp16 weights [N][K] (K-major), K index = tap * Cin_total + c.
+// D (fp32, TMEM) [128 rows = TN*TH*TW output pixels][BN output channels].
+struct GemmMaps {
+  CUtensorMap a[2][2];  // [source 0/1][hi/lo]
+  CUtensorMap b[2];     // [hi/lo]
+};
+
+struct GemmParams {
+  int nimg, H, W;  // output pixel grid (per phase plane for stride-2 inputs)
+  int TN, TH, TW;
+  int tiles_n, tiles_h, tiles_w;
+  int N;               // GEMM N (packed weight rows)
+  int kc;              // 64-wide channel chunks per tap (both sources)
+  int kc0;             // chunks taken from source 0
+  int num_taps;
+  int8_t tap_dh[9], tap_dw[9], tap_ph[9];
+  int split_k;
+  // epilogue
+  float* out_f32;          // [M][ldc] or null
+  __half* out_f16;         // [M][ldc16] or null (hi part)
+  __half* out_f16_lo;      // residual part for multi-pass consumers, or null
+  const float* bias;       // [N] or null
+  const float* rowbias;    // [nimg][N] or null (time embedding row per image)
+  const float* residual;   // [M][ldc] or null
+  int ldc;                 // row stride of out_f32 / residual (elements)
+  int ldc16;               // row stride of out_f16
+  int geglu;               // 1: columns are (x|gate) interleaved per tile, output width N/2
+  float* ws;               // split-K workspace [split][M][N]
+  // output pixel mapping: out row = ((n*OH + h*os + oa)*OW + w*os + ob)
+  int OH, OW, os, oa, ob;
+};
+
+struct GemmLaunch {
+  int BN, passes, stages;
+};
+
+void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream);
+void splitk_reduce_launch(const GemmParams& p, cudaStream_t stream);
+int gemm_tc_smem_bytes(int BN, int passes, int stages);
+
+}  // namespace sdb

@@ -1,0 +1,705 @@
+// kernels.cu — HBM-bound kernels around the tensor-core GEMMs: GroupNorm statistics, operand staging
+// (GroupNorm-apply + SiLU + fp16 hi/lo split, upsample / stride-2 phase layouts), LayerNorm, the
+// small CUDA-core convolutions (Cin = 4, Cout <= 4), sampler elementwise ops, weight packing.
+// All activations are NHWC; loads/stores are 8- or 16-byte vectors, coalesced along channels.
+#include "kernels.cuh"
+
+namespace sdb {
+
+static inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
+
+__device__ __forceinline__ void split_store8(const float (&f)[8], __half* hi, __half* lo) {
+  __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h);
+  if (lo) {
+    __half2 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<uint4*>(l);
+  }
+}
+
+// ============================================================ GroupNorm statistics
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x0, int C0,
+                                                       const float* __restrict__ x1, int C1, int HW, int pix_per_cta,
+                                                       double* __restrict__ sums) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int n = blockIdx.y;
+  const int C = C0 + C1, gs = C / 32;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  if (threadIdx.x < 32) s_sum[threadIdx.x] = 0.f, s_sq[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
+    const int c = cp * 2;
+    const float* ptr;
+    int stride;
+    if (c < C0) {
+      ptr = x0 + (size_t)n * HW * C0 + c;
+      stride = C0;
+    } else {
+      ptr = x1 + (size_t)n * HW * C1 + (c - C0);
+      stride = C1;
+    }
+    float s = 0.f, q = 0.f;
+    int p = p0;
+    for (; p + 4 <= p1; p += 4) {
+      float2 v0 = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
+      float2 v1 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 1) * stride);
+      float2 v2 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 2) * stride);
+      float2 v3 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 3) * stride);
+      s += (v0.x + v0.y) + (v1.x + v1.y) + (v2.x + v2.y) + (v3.x + v3.y);
+      q += (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) + (v2.x * v2.x + v2.y * v2.y) +
+           (v3.x * v3.x + v3.y * v3.y);
+    }
+    for (; p < p1; ++p) {
+      float2 v = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
+      s += v.x + v.y;
+      q += v.x * v.x + v.y * v.y;
+    }
+    const int g = c / gs;
+    atomicAdd(&s_sum[g], s);
+    atomicAdd(&s_sq[g], q);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&sums[((size_t)n * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+    atomicAdd(&sums[((size_t)n * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+}
+
+void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, cudaStream_t st) {
+  SDB_CHECK((C0 + C1) % 64 == 0 && C0 % 2 == 0, "GroupNorm channels");
+  int pix = (int)((((long long)HW * n) + 591) / 592);
+  if (pix < 16) pix = 16;
+  dim3 grid(ceil_div(HW, pix), n);
+  gn_stats_kernel<<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, pix, sums);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// per-(image, channel) affine from the group sums: y = x*scale + shift
+__device__ __forceinline__ void gn_affine(const double* sums, int n, int c, int gs, double inv_cnt, float eps,
+                                          const float* gamma, const float* beta, float& scale, float& shift) {
+  const int g = c / gs;
+  const double s = sums[((size_t)n * 32 + g) * 2 + 0], q = sums[((size_t)n * 32 + g) * 2 + 1];
+  const double mean = s * inv_cnt;
+  double var = q * inv_cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  scale = rstd * gamma[c];
+  shift = beta[c] - (float)mean * scale;
+}
+
+// ============================================================ operand staging
+__global__ void __launch_bounds__(256)
+prep_operand_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int H, int W,
+                    int pix_per_cta, int mode, const double* __restrict__ sums, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, __half* __restrict__ out_hi,
+                    __half* __restrict__ out_lo) {
+  extern __shared__ float s_aff[];  // scale[C], shift[C]
+  const int n = blockIdx.y;
+  const int C = C0 + C1, HW = H * W;
+  float* s_scale = s_aff;
+  float* s_shift = s_aff + C;
+  if (mode & PREP_NORM) {
+    const int gs = C / 32;
+    const double inv_cnt = 1.0 / ((double)gs * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) gn_affine(sums, n, c, gs, inv_cnt, eps, gamma, beta, s_scale[c], s_shift[c]);
+    __syncthreads();
+  }
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int c8n = C / 8;
+  const int items = (p1 - p0) * c8n;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int p = p0 + i / c8n;
+    const int c = (i % c8n) * 8;
+    const float* src = (c < C0) ? x0 + ((size_t)n * HW + p) * C0 + c : x1 + ((size_t)n * HW + p) * C1 + (c - C0);
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b = *reinterpret_cast<const float4*>(src + 4);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (mode & PREP_NORM) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * s_scale[c + j] + s_shift[c + j];
+    }
+    if (mode & PREP_SILU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+    const int h = p / W, w = p % W;
+    if (mode & PREP_UP2) {
+      const size_t base = (((size_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
+      const size_t rowstride = (size_t)2 * W * C;
+      split_store8(f, out_hi + base, out_lo ? out_lo + base : nullptr);
+      split_store8(f, out_hi + base + C, out_lo ? out_lo + base + C : nullptr);
+      split_store8(f, out_hi + base + rowstride, out_lo ? out_lo + base + rowstride : nullptr);
+      split_store8(f, out_hi + base + rowstride + C, out_lo ? out_lo + base + rowstride + C : nullptr);
+    } else if (mode & PREP_PHASE2) {
+      const int ph = (h & 1) * 2 + (w & 1);
+      const size_t o = ((((size_t)n * 4 + ph) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C + c;
+      split_store8(f, out_hi + o, out_lo ? out_lo + o : nullptr);
+    } else {
+      const size_t o = ((size_t)n * HW + p) * C + c;
+      split_store8(f, out_hi + o, out_lo ? out_lo + o : nullptr);
+    }
+  }
+}
+
+void prep_operand_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int mode,
+                         const double* sums, const float* gamma, const float* beta, float eps, Half2Ptr out,
+                         cudaStream_t st) {
+  const int C = C0 + C1, HW = H * W;
+  SDB_CHECK(C % 8 == 0 && C0 % 8 == 0, "operand channels must be multiples of 8");
+  int pix = (int)((((long long)HW * n) + 1183) / 1184);
+  if (pix < 8) pix = 8;
+  dim3 grid(ceil_div(HW, pix), n);
+  const size_t smem = (mode & PREP_NORM) ? (size_t)2 * C * sizeof(float) : 0;
+  prep_operand_kernel<<<grid, 256, smem, st>>>(x0, C0, x1, C1, H, W, pix, mode, sums, gamma, beta, eps, out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_f32_kernel(const float* __restrict__ x, int C, int HW, int silu, const double* __restrict__ sums,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y) {
+  const int n = blockIdx.y;
+  const int gs = C / 32;
+  const double inv_cnt = 1.0 / ((double)gs * HW);
+  const size_t total = (size_t)HW * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    float sc, sh;
+    gn_affine(sums, n, c, gs, inv_cnt, eps, gamma, beta, sc, sh);
+    float v = x[(size_t)n * total + i] * sc + sh;
+    y[(size_t)n * total + i] = silu ? silu_f(v) : v;
+  }
+}
+void gn_apply_f32_launch(const float* x, int C, int n, int HW, int silu, const double* sums, const float* gamma,
+                         const float* beta, float eps, float* y, cudaStream_t st) {
+  dim3 grid(ceil_div((long long)HW * C, 256 * 8), n);
+  gn_apply_f32_kernel<<<grid, 256, 0, st>>>(x, C, HW, silu, sums, gamma, beta, eps, y);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ LayerNorm: one warp per row
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                 float* __restrict__ out_f32) {
+  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int c8n = C / 8;
+  const float* xr = x + (size_t)row * C;
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c8 = lane + k * 32;
+    if (c8 < c8n) {
+      float4 a = *reinterpret_cast<const float4*>(xr + c8 * 8);
+      float4 b = *reinterpret_cast<const float4*>(xr + c8 * 8 + 4);
+      v[k][0] = a.x, v[k][1] = a.y, v[k][2] = a.z, v[k][3] = a.w, v[k][4] = b.x, v[k][5] = b.y, v[k][6] = b.z, v[k][7] = b.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c8 = lane + k * 32;
+    if (c8 < c8n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int c8 = lane + k * 32;
+    if (c8 < c8n) {
+      float f[8];
+      const int c = c8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (v[k][j] - mean) * rstd * gamma[c + j] + beta[c + j];
+      if (out_hi) split_store8(f, out_hi + (size_t)row * C + c, out_lo ? out_lo + (size_t)row * C + c : nullptr);
+      if (out_f32) {
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + c) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * C + c + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    }
+  }
+}
+void layernorm_launch(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                      Half2Ptr out, float* out_f32, cudaStream_t st) {
+  SDB_CHECK(C % 8 == 0 && C <= 1280, "LayerNorm width");
+  const int grid = ceil_div(rows, 8);
+  if (C <= 512)
+    layernorm_kernel<2><<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
+  else
+    layernorm_kernel<5><<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ conversions
+__global__ void convert_f16_kernel(const float* __restrict__ x, long long count8, __half* __restrict__ hi,
+                                   __half* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count8; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = *reinterpret_cast<const float4*>(x + i * 8);
+    float4 b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    split_store8(f, hi + i * 8, lo ? lo + i * 8 : nullptr);
+  }
+}
+void convert_f16_launch(const float* x, long long count, Half2Ptr out, cudaStream_t st) {
+  SDB_CHECK(count % 8 == 0, "convert count");
+  const long long c8 = count / 8;
+  int grid = (int)((c8 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  convert_f16_kernel<<<grid, 256, 0, st>>>(x, c8, out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ y, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const long long r = i / C;
+    const int p = int(r % HW);
+    const long long n = r / HW;
+    y[i] = x[(n * C + c) * HW + p];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ y, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = int(i % HW);
+    const long long r = i / HW;
+    const int c = int(r % C);
+    const long long n = r / C;
+    y[i] = x[(n * HW + p) * C + c];
+  }
+}
+void nchw_to_nhwc_launch(const float* x, int n, int C, int H, int W, float* y, cudaStream_t st) {
+  const long long total = (long long)n * C * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(x, C, H * W, y, total);
+  SDB_CUDA(cudaGetLastError());
+}
+void nhwc_to_nchw_launch(const float* x, int n, int C, int H, int W, float* y, cudaStream_t st) {
+  const long long total = (long long)n * C * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(x, C, H * W, y, total);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ conv 3x3, Cin = 4 (fp32, CUDA cores)
+// block = 64 pixels x (Cout/..) ; thread (pix, co-lane): weights staged in smem as [36][Cout]
+__global__ void __launch_bounds__(256)
+conv3x3_cin4_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w, const float* __restrict__ b,
+                    int Cout, const float* __restrict__ pre_w, const float* __restrict__ pre_b, float pre_scale,
+                    float* __restrict__ y) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                  // [36][Cout]
+  float* s_in = sm + 36 * Cout;     // [PIX][36]
+  constexpr int PIX = 32;
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * PIX;
+  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) {
+    const int k = i / Cout, co = i % Cout;  // k = ci*9 + tap (OIHW inner order)
+    s_w[i] = w[(size_t)co * 36 + k];
+  }
+  for (int i = threadIdx.x; i < PIX * 36; i += blockDim.x) {
+    const int pl = i / 36, k = i % 36;
+    const int ci = k / 9, tap = k % 9;
+    const int p = p0 + pl;
+    float v = 0.f;
+    if (p < HW) {
+      const int h = p / W + tap / 3 - 1, ww = p % W + tap % 3 - 1;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) {
+        const float* xp = x + (size_t)n * 4 * HW + (size_t)h * W + ww;
+        if (pre_w) {
+          float acc = pre_b[ci];
+#pragma unroll
+          for (int cj = 0; cj < 4; ++cj) acc += pre_w[ci * 4 + cj] * (xp[(size_t)cj * HW] * pre_scale);
+          v = acc;
+        } else {
+          v = xp[(size_t)ci * HW];
+        }
+      }
+    }
+    s_in[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PIX * Cout; i += blockDim.x) {
+    const int pl = i / Cout, co = i % Cout;
+    const int p = p0 + pl;
+    if (p >= HW) continue;
+    float acc = b ? b[co] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc += s_in[pl * 36 + k] * s_w[k * Cout + co];
+    y[((size_t)n * HW + p) * Cout + co] = acc;
+  }
+}
+void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* w, const float* b, int Cout,
+                         const float* pre_w, const float* pre_b, float pre_scale, float* y, cudaStream_t st) {
+  const size_t smem = (size_t)(36 * Cout + 32 * 36) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    SDB_CUDA(cudaFuncSetAttribute(conv3x3_cin4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  dim3 grid(ceil_div(H * W, 32), n);
+  conv3x3_cin4_kernel<<<grid, 256, smem, st>>>(x_nchw, H, W, w, b, Cout, pre_w, pre_b, pre_scale, y);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ conv 3x3, Cout <= 4, fused GroupNorm + SiLU
+// one warp per output pixel; lanes split the channels (float4), warp-shuffle reduction.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, const double* __restrict__ sums,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                          const float* __restrict__ wp, const float* __restrict__ b, float* __restrict__ y) {
+  extern __shared__ float sm[];
+  float* s_scale = sm;      // [C]
+  float* s_shift = sm + C;  // [C]
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  {
+    const int gs = C / 32;
+    const double inv_cnt = 1.0 / ((double)gs * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) gn_affine(sums, n, c, gs, inv_cnt, eps, gamma, beta, s_scale[c], s_shift[c]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int c4n = C / 4;
+  for (int p = blockIdx.x * wpb + warp; p < HW; p += gridDim.x * wpb) {
+    const int h = p / W, w = p % W;
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;  // warp-uniform
+      const float* xp = x + ((size_t)n * HW + (size_t)hh * W + ww) * C;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const int c = c4 * 4;
+        float4 v = *reinterpret_cast<const float4*>(xp + c);
+        float f0 = silu_f(v.x * s_scale[c] + s_shift[c]);
+        float f1 = silu_f(v.y * s_scale[c + 1] + s_shift[c + 1]);
+        float f2 = silu_f(v.z * s_scale[c + 2] + s_shift[c + 2]);
+        float f3 = silu_f(v.w * s_scale[c + 3] + s_shift[c + 3]);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          float4 wv = *reinterpret_cast<const float4*>(wp + ((size_t)o * 9 + tap) * C + c);
+          acc[o] += f0 * wv.x + f1 * wv.y + f2 * wv.z + f3 * wv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) y[((size_t)n * COUT + o) * HW + p] = acc[o] + b[o];
+    }
+  }
+}
+void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const double* sums, const float* gamma,
+                               const float* beta, float eps, const float* w_packed, const float* b, int Cout,
+                               float* y_nchw, cudaStream_t st) {
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  int gx = ceil_div(H * W, 8);
+  if (gx > 148 * 8) gx = 148 * 8;
+  dim3 grid(gx, n);
+  if (Cout == 4)
+    conv3x3_small_cout_kernel<4><<<grid, 256, smem, st>>>(x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
+  else if (Cout == 3)
+    conv3x3_small_cout_kernel<3><<<grid, 256, smem, st>>>(x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
+  else
+    throw Error("conv3x3_small_cout: Cout must be 3 or 4");
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ time embedding + GEMV
+// single CTA: t_emb -> lin1 -> silu -> lin2 -> silu(emb) (every consumer applies SiLU first)
+__global__ void __launch_bounds__(1024)
+time_embed_kernel(int t, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                  const float* __restrict__ b2, float* __restrict__ emb_silu) {
+  __shared__ float s_t[320];
+  __shared__ float s_h[1280];
+  const int tid = threadIdx.x;
+  if (tid < 160) {
+    // reference unet/mod.rs:24-29: freqs = exp(arange(half) * (-ln(10000)/half)); args = t*freqs; [cos | sin]
+    const float f = expf((float)tid * (float)(-9.210340371976184 / 160.0));
+    const float a = (float)t * f;
+    s_t[tid] = cosf(a);
+    s_t[160 + tid] = sinf(a);
+  }
+  __syncthreads();
+  for (int o = tid; o < 1280; o += blockDim.x) {
+    float acc = b1[o];
+    for (int k = 0; k < 320; ++k) acc += s_t[k] * w1[(size_t)k * 1280 + o];
+    s_h[o] = silu_f(acc);
+  }
+  __syncthreads();
+  for (int o = tid; o < 1280; o += blockDim.x) {
+    float acc = b2[o];
+    for (int k = 0; k < 1280; ++k) acc += s_h[k] * w2[(size_t)k * 1280 + o];
+    emb_silu[o] = silu_f(acc);
+  }
+}
+void time_embed_launch(int t, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
+                       cudaStream_t st) {
+  time_embed_kernel<<<1, 1024, 0, st>>>(t, w1, b1, w2, b2, emb_silu);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// y[N] = x[K] W[K][N] + b ; block handles 128 outputs, 8 k-slices reduced through smem
+__global__ void __launch_bounds__(256)
+gemv_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, int K, int N,
+            float* __restrict__ y) {
+  __shared__ float s_part[8][32];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ks = threadIdx.x >> 5;  // 0..7
+  float acc = 0.f;
+  if (col < N)
+    for (int k = ks; k < K; k += 8) acc += x[k] * W[(size_t)k * N + col];
+  s_part[ks][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ks == 0 && col < N) {
+    float s = b ? b[col] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += s_part[j][threadIdx.x & 31];
+    y[col] = s;
+  }
+}
+void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st) {
+  gemv_kernel<<<ceil_div(N, 32), 256, 0, st>>>(x, W, b, K, N, y);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ sampler elementwise
+__global__ void cfg_ddim_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ lat,
+                                long long count, float scale, float sqrt_1m_at, float inv_sqrt_at, float sqrt_aprev,
+                                float dir_coef) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float u = eu[i], c = ec[i];
+    const float pred = u + (c - u) * scale;               // stablediffusion/mod.rs:190-191
+    const float x0 = (lat[i] - pred * sqrt_1m_at) * inv_sqrt_at;  // :152
+    lat[i] = x0 * sqrt_aprev + pred * dir_coef;           // :153-155 (sigma = 0)
+  }
+}
+void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long long count, float scale,
+                     float sqrt_one_minus_at, float inv_sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st) {
+  int grid = (int)((count + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  cfg_ddim_kernel<<<grid, 256, 0, st>>>(eps_u, eps_c, latent, count, scale, sqrt_one_minus_at, inv_sqrt_at, sqrt_aprev, dir_coef);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void to_rgb8_kernel(const float* __restrict__ img, int HW, long long total, uint8_t* __restrict__ rgb) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % 3);
+    const long long r = i / 3;
+    const int p = int(r % HW);
+    const long long n = r / HW;
+    float v = img[(n * 3 + c) * HW + p];
+    v = (v + 1.0f) / 2.0f * 255.0f;             // stablediffusion/mod.rs:79-84
+    // :96  v.to_f64().min(255.0).max(0.0) as u8  (NaN -> min gives 255)
+    float m = (v != v) ? 255.0f : fminf(v, 255.0f);
+    m = fmaxf(m, 0.0f);
+    rgb[i] = (uint8_t)m;                        // truncation toward zero
+  }
+}
+void to_rgb8_launch(const float* img_nchw, int n, int H, int W, uint8_t* rgb, cudaStream_t st) {
+  const long long total = (long long)n * 3 * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  to_rgb8_kernel<<<grid, 256, 0, st>>>(img_nchw, H * W, total, rgb);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void scale_kernel(const float* __restrict__ x, float s, long long count, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * s;
+}
+void scale_launch(const float* x, float s, long long count, float* y, cudaStream_t st) {
+  int grid = (int)((count + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  scale_kernel<<<grid, 256, 0, st>>>(x, s, count, y);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__global__ void randn_kernel(float* __restrict__ x, long long count, uint32_t k0, uint32_t k1) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = mix32((uint32_t)i ^ k0), b = mix32(((uint32_t)i * 0x9E3779B9u) ^ k1);
+    const float u1 = ((a >> 8) + 1) * (1.0f / 16777216.0f);  // (0,1]
+    const float u2 = (b >> 8) * (1.0f / 16777216.0f);
+    x[i] = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+  }
+}
+void randn_launch(float* x, long long count, uint64_t seed, cudaStream_t st) {
+  int grid = (int)((count + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  randn_kernel<<<grid, 256, 0, st>>>(x, count, (uint32_t)seed * 2654435761u + 1u, (uint32_t)(seed >> 32) ^ 0x5bd1e995u);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ weight packing
+__device__ __forceinline__ void split_store1(float f, __half* hi, __half* lo, size_t o) {
+  const __half h = __float2half_rn(f);
+  hi[o] = h;
+  if (lo) lo[o] = __float2half_rn(f - __half2float(h));
+}
+__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, __half* hi, __half* lo) {
+  const long long total = (long long)Cout * kk * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    const long long r = i / Cin;
+    const int tap = int(r % kk);
+    const long long co = r / kk;
+    split_store1(w[(co * Cin + c) * kk + tap], hi, lo, (size_t)i);
+  }
+}
+void pack_conv_launch(const float* w, int Cout, int Cin, int ksize, Half2Ptr out, cudaStream_t st) {
+  const long long total = (long long)Cout * ksize * ksize * Cin;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_conv_kernel<<<grid, 256, 0, st>>>(w, Cout, Cin, ksize * ksize, out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// nearest-2x upsample folded into the following 3x3 conv: output phase (a,b) in {0,1}^2 sees a 2x2 window of
+// the low-res source; window tap (i,j) accumulates the 3x3 taps that land on the same source pixel:
+//   a=0: rows {0} -> i=0, {1,2} -> i=1 ;  a=1: rows {0,1} -> i=0, {2} -> i=1   (same for columns)
+__global__ void pack_conv_up2_kernel(const float* __restrict__ w, int Cout, int Cin, __half* hi, __half* lo) {
+  const long long total = (long long)4 * Cout * 4 * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    long long r = i / Cin;
+    const int wt = int(r % 4);
+    r /= 4;
+    const int co = int(r % Cout);
+    const int phase = int(r / Cout);
+    const int a = phase >> 1, b = phase & 1, ti = wt >> 1, tj = wt & 1;
+    float acc = 0.f;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ii = (a == 0) ? (kh == 0 ? 0 : 1) : (kh == 2 ? 1 : 0);
+      if (ii != ti) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int jj = (b == 0) ? (kw == 0 ? 0 : 1) : (kw == 2 ? 1 : 0);
+        if (jj != tj) continue;
+        acc += w[(((size_t)co * Cin + c) * 3 + kh) * 3 + kw];
+      }
+    }
+    split_store1(acc, hi, lo, (size_t)i);
+  }
+}
+void pack_conv_up2_launch(const float* w, int Cout, int Cin, Half2Ptr out, cudaStream_t st) {
+  const long long total = (long long)16 * Cout * Cin;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_conv_up2_kernel<<<grid, 256, 0, st>>>(w, Cout, Cin, out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out, __half* hi, __half* lo, int row_offset) {
+  // tiled transpose [in][out] -> [out][in]
+  __shared__ float tile[32][33];
+  const int o0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, o = o0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < in && o < out) ? w[(size_t)i * out + o] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int o = o0 + r, i = i0 + threadIdx.x;
+    if (o < out && i < in) split_store1(tile[threadIdx.x][r], hi, lo, (size_t)(row_offset + o) * in + i);
+  }
+}
+void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st) {
+  dim3 grid(ceil_div(out, 32), ceil_div(in, 32)), block(32, 8);
+  pack_linear_kernel<<<grid, block, 0, st>>>(w, in, out, dst.hi, dst.lo, row_offset);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ b, int in, int h4, int half_tile,
+                                  __half* hi, __half* lo, float* bias_packed) {
+  // packed row pr in [0, 2*h4): tile j = pr / (2*half_tile); within tile q = pr % (2*half_tile);
+  // q < half_tile -> x column j*half_tile + q ; else gate column h4 + j*half_tile + (q - half_tile)
+  const long long total = (long long)2 * h4 * in;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = int(idx % in);
+    const int pr = int(idx / in);
+    const int j = pr / (2 * half_tile), q = pr % (2 * half_tile);
+    const int col = (q < half_tile) ? j * half_tile + q : h4 + j * half_tile + (q - half_tile);
+    split_store1(w[(size_t)i * (2 * h4) + col], hi, lo, (size_t)idx);
+    if (i == 0) bias_packed[pr] = b[col];
+  }
+}
+void pack_geglu_launch(const float* w, const float* b, int in, int h4, int half_tile, Half2Ptr dst, float* bias_packed,
+                       cudaStream_t st) {
+  const long long total = (long long)2 * h4 * in;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_geglu_kernel<<<grid, 256, 0, st>>>(w, b, in, h4, half_tile, dst.hi, dst.lo, bias_packed);
+  SDB_CUDA(cudaGetLastError());
+}
+
+__global__ void pack_small_cout_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ out) {
+  const int total = Cout * 9 * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cin, tap = (i / Cin) % 9, co = i / (9 * Cin);
+    out[i] = w[((size_t)co * Cin + c) * 9 + tap];
+  }
+}
+void pack_small_cout_launch(const float* w, int Cout, int Cin, float* out, cudaStream_t st) {
+  pack_small_cout_kernel<<<ceil_div(Cout * 9 * Cin, 256), 256, 0, st>>>(w, Cout, Cin, out);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ synthetic weights
+__global__ void synth_fill_kernel(float* __restrict__ dst, long long count, uint32_t key, float bound, float offset) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t h = mix32((uint32_t)i ^ key);
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    // (u*2 - 1) is exact; one rounding for *bound, one for +offset — same as the numpy generator
+    dst[i] = __fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(u, 2.0f), 1.0f), bound), offset);
+  }
+}
+void synth_fill_launch(float* dst, long long count, uint32_t key, float bound, float offset, cudaStream_t st) {
+  int grid = (int)((count + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  synth_fill_kernel<<<grid, 256, 0, st>>>(dst, count, key, bound, offset);
+  SDB_CUDA(cudaGetLastError());
+}
+
+}  // namespace sdb

@@ -1,0 +1,117 @@
+// model_def.cuh — weight tree of the hot path. Tensor names are the reference's dump-dir paths
+// (src/model/unet/load.rs:213-306, src/model/autoencoder/load.rs:16-198).
+#pragma once
+#include <memory>
+
+#include "runtime.cuh"
+
+namespace sdb {
+
+struct ConvW {
+  int cin = 0, cout = 0, k = 0;
+  int wi = -1, bi = -1;     // registry indices (weight, bias)
+  WeightOp packed;          // [cout][k*k*cin] fp16 hi/lo (or 4 folded-upsample phases)
+  float* bias = nullptr;    // device pointer into the master arena
+  float* w_small = nullptr; // fp32 [cout][9][cin] for Cout <= 4
+  int passes = 1;
+};
+struct LinW {
+  int in = 0, out = 0;
+  int wi = -1, bi = -1;
+  WeightOp packed;  // [out][in]
+  float* bias = nullptr;
+  int passes = 1;
+};
+struct NormW {
+  int c = 0;
+  int gi = -1, bi = -1;
+  float* gamma = nullptr;
+  float* beta = nullptr;
+};
+struct ResBlockW {
+  int cin = 0, cout = 0;
+  NormW norm_in, norm_out;
+  ConvW conv_in, conv_out, skip;
+  LinW lin_embed;
+  bool has_skip = false;
+  int emb_off = 0;  // offset of this block's row in the fused time-embedding GEMV output
+  int passes = 1;
+};
+struct AttnW {
+  LinW query, key, value, out;
+};
+struct SpatialTransformerW {
+  int c = 0, heads = 8, d = 0, dpad = 0;
+  NormW norm, ln1, ln2, ln3;
+  ConvW proj_in, proj_out;
+  AttnW attn1, attn2;
+  LinW geglu, ff;
+  // fused / re-laid-out projections
+  WeightOp w_qk1;      // [2*heads*dpad][c]   self-attention q|k, head-padded
+  WeightOp w_v1;       // [c][c]              value, used as the A operand -> V^T
+  WeightOp w_q2;       // [heads*dpad][c]     cross-attention q
+  WeightOp w_k2;       // [heads*dpad][768]   cross-attention k (context)
+  WeightOp w_v2;       // [c][768]            cross-attention v as the A operand -> V^T
+  WeightOp w_o1, w_o2; // [c][heads*d] out projections (un-padded input)
+  WeightOp w_geglu;    // [8c][c] tile-interleaved x|gate
+  float* geglu_bias = nullptr;  // packed order
+  int passes = 1;
+};
+enum BlockKind : int { BK_CONV = 0, BK_DOWN, BK_R, BK_RT, BK_RU, BK_RTU };
+struct UNetBlockW {
+  int kind = BK_R, cin = 0, cout = 0;
+  ConvW conv;  // BK_CONV / BK_DOWN / upsample conv
+  ResBlockW res;
+  SpatialTransformerW st;
+  int level = 0;  // 0: H, 1: H/2, 2: H/4, 3: H/8 (resolution at which the block's ResBlock runs)
+};
+struct ResnetW {
+  int cin = 0, cout = 0;
+  NormW norm1, norm2;
+  ConvW conv1, conv2, nin;
+  bool has_nin = false;
+  int passes = 1;
+};
+struct VaeAttnW {
+  NormW norm;
+  ConvW q, k, v, proj_out;
+  int passes = 1;
+};
+struct DecoderBlockW {
+  ResnetW res[3];
+  bool has_up = false;
+  ConvW up;
+};
+
+struct Model {
+  // UNet
+  LinW lin1_time, lin2_time;
+  std::vector<UNetBlockW> in_blocks, out_blocks;
+  ResBlockW mid_res1, mid_res2;
+  SpatialTransformerW mid_st;
+  NormW norm_out;
+  ConvW conv_out;
+  std::vector<ResBlockW*> resblocks;     // all 22, in execution order
+  std::vector<SpatialTransformerW*> sts; // all 16, in execution order
+  float* emb_w_all = nullptr;            // fp32 [1280][emb_total]: every lin_embed side by side
+  float* emb_b_all = nullptr;            // fp32 [emb_total]: lin_embed bias + conv_in bias
+  int emb_total = 0;
+  // VAE decoder
+  ConvW post_quant, vae_conv_in, vae_conv_out;
+  ResnetW mid_block1, mid_block2;
+  VaeAttnW mid_attn;
+  DecoderBlockW dec[4];
+  NormW vae_norm_out;
+  // sampler
+  int alphas_i = -1;
+  std::vector<float> alphas_host;
+  // graphs (keyed by shape)
+  struct GraphEntry {
+    long long key;
+    cudaGraphExec_t exec;
+    void* io[8];
+  };
+  std::vector<GraphEntry> graphs;
+};
+
+}  // namespace sdb

@@ -1,0 +1,280 @@
+// runtime.cu — context plumbing, TMA tensor maps and the GEMM op builder.
+#include "runtime.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
+namespace sdb {
+
+// ------------------------------------------------------------------ arena
+void Arena::init(size_t bytes) {
+  SDB_CUDA(cudaMalloc(&base, bytes));
+  cap = bytes;
+  off = 0;
+}
+void Arena::destroy() {
+  if (base) cudaFree(base);
+  base = nullptr;
+  cap = off = 0;
+}
+void* Arena::alloc(size_t bytes) {
+  const size_t a = (off + 1023) & ~size_t(1023);
+  if (a + bytes > cap)
+    throw Error("arena exhausted: need " + std::to_string(a + bytes) + " of " + std::to_string(cap) + " bytes");
+  off = a + bytes;
+  if (off > high) high = off;
+  return base + a;
+}
+
+float* Ctx::master_ptr(const std::string& name) {
+  auto it = index.find(name);
+  if (it == index.end()) throw Error("unknown tensor: " + name);
+  return reinterpret_cast<float*>(master.base) + tensors[it->second].offset;
+}
+const TensorInfo& Ctx::info(const std::string& name) {
+  auto it = index.find(name);
+  if (it == index.end()) throw Error("unknown tensor: " + name);
+  return tensors[it->second];
+}
+
+const char* kernel_class_name(int cls) {
+  static const char* names[KC_COUNT] = {"gemm_tc", "splitk_reduce", "attention", "gn_stats", "prep_operand",
+                                        "layernorm", "small_conv", "elementwise"};
+  return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
+}
+
+// ------------------------------------------------------------------ profiling scope
+KernelScope::KernelScope(Ctx& c_, int cls_, double flops, double bytes) : c(c_), cls(cls_), on(c_.profiling) {
+  c.launches++;
+  c.cls_launches[cls]++;
+  c.cls_flops[cls] += flops;
+  c.cls_bytes[cls] += bytes;
+  if (on) {
+    ev.cls = cls;
+    ev.flops = flops;
+    ev.bytes = bytes;
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, c.stream);
+  }
+}
+KernelScope::~KernelScope() {
+  if (on) {
+    cudaEventRecord(ev.b, c.stream);
+    c.prof.push_back(ev);
+  }
+}
+void profile_collect(Ctx& c) {
+  if (c.prof.empty()) return;
+  cudaStreamSynchronize(c.stream);
+  for (auto& e : c.prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    c.cls_ms[e.cls] += ms;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  c.prof.clear();
+}
+
+// ------------------------------------------------------------------ tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* p = nullptr;
+    SDB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) throw Error("cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// fp16 tensor [N][P][H][W][C]; box {64, bw, bh, 1, bn}; 128B swizzle; zero fill outside
+static CUtensorMap make_act_map(const __half* ptr, int C, int W, int H, int P, int N, int bw, int bh, int bn) {
+  CUtensorMap m;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)P * H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(act) failed: " + std::to_string((int)r));
+  return m;
+}
+// fp16 matrix [rows][K]; box {64, brows}
+static CUtensorMap make_w_map(const __half* ptr, int K, int rows, int brows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)brows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weight) failed: " + std::to_string((int)r));
+  return m;
+}
+
+static int pow2_floor(int x) {
+  int p = 1;
+  while (p * 2 <= x) p *= 2;
+  return p;
+}
+static int pow2_ceil(int x) {
+  int p = 1;
+  while (p < x) p *= 2;
+  return p;
+}
+
+// ------------------------------------------------------------------ GEMM op
+void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const WeightOp& w, int passes, const Epilogue& ep) {
+  ActOp a0 = a0in, a1;
+  if (a1in) a1 = *a1in;
+  if (kind == G_CONV1) {  // a 1x1 conv over NHWC is a plain row-major GEMM
+    a0.W = a0.n * a0.H * a0.W, a0.H = 1, a0.n = 1;
+    if (a1in) a1.W = a1.n * a1.H * a1.W, a1.H = 1, a1.n = 1;
+    kind = G_LINEAR;
+  }
+  SDB_CHECK(a0.C % 64 == 0, "A channels must be a multiple of 64");
+  SDB_CHECK(!a1in || a1.C % 64 == 0, "A1 channels must be a multiple of 64");
+  if (c.opt_precision >= 1 && c.opt_precision <= 3) passes = c.opt_precision;
+  SDB_CHECK(passes >= 1 && passes <= 3, "passes");
+  SDB_CHECK(passes < 2 || a0.p.lo, "multi-pass GEMM needs the lo half of A");
+  SDB_CHECK(passes < 2 || !a1in || a1.p.lo, "multi-pass GEMM needs the lo half of A1");
+  SDB_CHECK(passes < 3 || w.p.lo, "3-pass GEMM needs the lo half of W");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Ctot = a0.C + (a1in ? a1.C : 0);
+  p.nimg = a0.n, p.H = a0.H, p.W = a0.W;
+  p.N = w.N;
+  p.kc = Ctot / 64;
+  p.kc0 = a0.C / 64;
+  int phases_out = 1;
+  switch (kind) {
+    case G_LINEAR:
+      p.num_taps = 1;
+      break;
+    case G_CONV3:
+      p.num_taps = 9;
+      for (int t = 0; t < 9; ++t) p.tap_dh[t] = t / 3 - 1, p.tap_dw[t] = t % 3 - 1, p.tap_ph[t] = 0;
+      break;
+    case G_CONV3_S2:
+      SDB_CHECK(a0.P == 4, "stride-2 conv needs a 4-phase operand");
+      p.num_taps = 9;
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t % 3;
+        p.tap_dh[t] = kh == 0 ? -1 : 0;
+        p.tap_dw[t] = kw == 0 ? -1 : 0;
+        p.tap_ph[t] = (kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0);
+      }
+      break;
+    case G_CONV3_UP2:
+      p.num_taps = 4;
+      phases_out = 4;
+      break;
+    default:
+      throw Error("bad gemm kind");
+  }
+  SDB_CHECK(w.K == p.num_taps * Ctot, "weight K does not match the operand");
+
+  // M tile = TN x TH x TW output pixels
+  p.TW = std::min(pow2_floor(a0.W), 128);
+  p.TH = std::min(128 / p.TW, pow2_ceil(a0.H));
+  p.TN = 128 / (p.TW * p.TH);
+  p.tiles_w = (a0.W + p.TW - 1) / p.TW;
+  p.tiles_h = (a0.H + p.TH - 1) / p.TH;
+  p.tiles_n = (a0.n + p.TN - 1) / p.TN;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  // N tile
+  int BN;
+  if (ep.geglu)
+    BN = 128;
+  else if (w.N % 128 == 0)
+    BN = (w.N % 256 == 0 && (long long)m_tiles * (w.N / 256) >= 296) ? 256 : 128;
+  else if (w.N % 160 == 0)
+    BN = 160;
+  else
+    BN = 64;
+  const int n_tiles = (w.N + BN - 1) / BN;
+
+  // split-K when the grid cannot fill the machine and the K loop is long
+  const int iters = p.num_taps * p.kc;
+  int split = 1;
+  if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
+    const int ctas = m_tiles * n_tiles;
+    if (ctas < 112 && iters >= 16) {
+      split = std::min(std::min((148 + ctas - 1) / ctas, iters / 8), 16);
+      if (split < 1) split = 1;
+    }
+  }
+  p.split_k = split;
+
+  p.out_f32 = ep.out_f32;
+  p.out_f16 = ep.out_f16.hi;
+  p.out_f16_lo = ep.out_f16.lo;
+  p.bias = ep.bias;
+  p.rowbias = ep.rowbias;
+  p.residual = ep.residual;
+  p.geglu = ep.geglu;
+  const int nout = ep.geglu ? w.N / 2 : w.N;
+  p.ldc = ep.ldc ? ep.ldc : nout;
+  p.ldc16 = ep.ldc16 ? ep.ldc16 : nout;
+  p.os = (kind == G_CONV3_UP2) ? 2 : 1;
+  p.OH = a0.H * p.os, p.OW = a0.W * p.os;
+
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  maps.a[0][0] = make_act_map(a0.p.hi, a0.C, a0.W, a0.H, a0.P, a0.n, p.TW, p.TH, p.TN);
+  maps.a[0][1] = maps.a[0][0];
+  if (passes >= 2) maps.a[0][1] = make_act_map(a0.p.lo, a0.C, a0.W, a0.H, a0.P, a0.n, p.TW, p.TH, p.TN);
+  maps.a[1][0] = maps.a[0][0];
+  maps.a[1][1] = maps.a[0][1];
+  if (a1in) {
+    SDB_CHECK(a1.n == a0.n && a1.H == a0.H && a1.W == a0.W && a1.P == a0.P, "concat operand geometry");
+    maps.a[1][0] = make_act_map(a1.p.hi, a1.C, a1.W, a1.H, a1.P, a1.n, p.TW, p.TH, p.TN);
+    maps.a[1][1] = maps.a[1][0];
+    if (passes >= 2) maps.a[1][1] = make_act_map(a1.p.lo, a1.C, a1.W, a1.H, a1.P, a1.n, p.TW, p.TH, p.TN);
+  }
+
+  const double Mtot = (double)a0.n * a0.H * a0.W;
+  const double flops = 2.0 * Mtot * (double)w.N * (double)w.K;  // algorithmic (one product per MAC)
+  const double bytes = Mtot * Ctot * 2.0 + (double)w.N * w.K * 2.0 + Mtot * nout * 4.0;
+
+  for (int phase = 0; phase < phases_out; ++phase) {
+    const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
+    const __half* wlo = w.p.lo ? w.p.lo + (size_t)phase * w.N * w.K : nullptr;
+    maps.b[0] = make_w_map(whi, w.K, w.N, BN);
+    maps.b[1] = maps.b[0];
+    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, w.N, BN);
+    if (kind == G_CONV3_UP2) {
+      const int a = phase >> 1, b = phase & 1;
+      p.oa = a, p.ob = b;
+      for (int t = 0; t < 4; ++t) {
+        const int ti = t >> 1, tj = t & 1;
+        p.tap_dh[t] = (a == 0) ? (ti == 0 ? -1 : 0) : (ti == 0 ? 0 : 1);
+        p.tap_dw[t] = (b == 0) ? (tj == 0 ? -1 : 0) : (tj == 0 ? 0 : 1);
+        p.tap_ph[t] = 0;
+      }
+    }
+    if (split > 1) {
+      const size_t need = (size_t)split * (size_t)Mtot * w.N * sizeof(float);
+      p.ws = reinterpret_cast<float*>(c.work.alloc(need));
+    }
+    {
+      KernelScope ks(c, KC_GEMM, flops, bytes);  // executed FLOPs of this launch (2*M*N*K)
+      gemm_tc_launch(maps, p, BN, passes, c.stream);
+    }
+    if (split > 1) {
+      KernelScope ks(c, KC_SPLITK, 0, (double)split * Mtot * w.N * 4.0);
+      splitk_reduce_launch(p, c.stream);
+    }
+  }
+}
+
+}  // namespace sdb

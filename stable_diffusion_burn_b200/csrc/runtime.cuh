@@ -1,0 +1,119 @@
+// runtime.cuh — context, arenas, weight registry, tensor-map construction, GEMM op builder.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace sdb {
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  void init(size_t bytes);
+  void destroy();
+  void* alloc(size_t bytes);
+  template <class T>
+  T* get(size_t count) {
+    return reinterpret_cast<T*>(alloc(count * sizeof(T)));
+  }
+  void reset() { off = 0; }
+};
+
+struct TensorInfo {
+  std::string name;
+  int64_t dims[4] = {1, 1, 1, 1};
+  int ndim = 0;
+  size_t offset = 0;  // float offset in the master arena
+  int64_t count = 0;
+  int kind = 0;       // 0 conv_w 1 conv_b 2 lin_w 3 lin_b 4 norm_g 5 norm_b 6 schedule
+  int fan_in = 1;
+};
+
+enum KernelClass : int {
+  KC_GEMM = 0,
+  KC_SPLITK,
+  KC_ATTN,
+  KC_GN_STATS,
+  KC_PREP,
+  KC_LAYERNORM,
+  KC_SMALLCONV,
+  KC_ELEMENTWISE,
+  KC_COUNT
+};
+
+struct ProfEvent {
+  int cls;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+
+// fp16 activation operand [n][P][H][W][C]
+struct ActOp {
+  Half2Ptr p;
+  int n = 1, P = 1, H = 1, W = 1, C = 0;
+};
+// packed weight [N][K]
+struct WeightOp {
+  Half2Ptr p;
+  int N = 0, K = 0;
+};
+enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4 };
+
+struct Epilogue {
+  float* out_f32 = nullptr;
+  Half2Ptr out_f16;
+  const float* bias = nullptr;
+  const float* rowbias = nullptr;
+  const float* residual = nullptr;
+  int geglu = 0;
+  int ldc = 0;    // 0 -> N (or N/2 for geglu)
+  int ldc16 = 0;  // 0 -> N (or N/2 for geglu)
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  Arena master, packed, work;
+  std::vector<TensorInfo> tensors;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  // options
+  int opt_precision = 0;  // 0 = per-layer policy, 1/2/3 = force
+  int opt_graphs = 1;
+  int opt_splitk = 1;
+  // profiling
+  bool profiling = false;
+  std::vector<ProfEvent> prof;
+  int64_t launches = 0;
+  double cls_ms[KC_COUNT] = {0}, cls_flops[KC_COUNT] = {0}, cls_bytes[KC_COUNT] = {0};
+  int64_t cls_launches[KC_COUNT] = {0};
+  void* model = nullptr;  // Model* (model.cu)
+
+  float* master_ptr(const std::string& name);
+  const TensorInfo& info(const std::string& name);
+  bool has(const std::string& name) const { return index.count(name) != 0; }
+};
+
+struct KernelScope {  // RAII: counts a launch, optionally brackets it with events
+  Ctx& c;
+  int cls;
+  bool on;
+  ProfEvent ev;
+  KernelScope(Ctx& c, int cls, double flops = 0, double bytes = 0);
+  ~KernelScope();
+};
+void profile_collect(Ctx& c);
+
+// one tcgen05 GEMM / implicit conv (+ split-K reduction when chosen)
+//   a0 (+a1 = channel concat), geometry kind, weights, passes (1..3), epilogue
+void run_gemm(Ctx& c, int kind, const ActOp& a0, const ActOp* a1, const WeightOp& w, int passes, const Epilogue& ep);
+
+const char* kernel_class_name(int cls);
+
+}  // namespace sdb

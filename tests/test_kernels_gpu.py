@@ -1,0 +1,92 @@
+"""GPU parity of the individual kernels, called through the C ABI, against torch-CPU fp32 references
+of the same op (the op definitions the oracle uses)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# tolerance per number of tensor-core passes (relative L2): 1 pass = fp16 operand rounding,
+# 2 = activations exact, 3 = fp32-class
+TOL = {1: 1.0e-3, 2: 8.0e-4, 3: 2.0e-5}
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def rnd(shape, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("passes", [1, 2, 3])
+@pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 2560, 1280), (77, 64, 64), (4096, 128, 512),
+                                    (19072, 128, 512), (1, 768, 640), (1000, 1280, 960)])
+def test_linear(ctx, M, K, N, passes):
+    a = rnd((M, K), 1); w = rnd((K, N), 2, K ** -0.5); b = rnd((N,), 3)
+    ref = a.astype(np.float64) @ w.astype(np.float64) + b
+    out = ctx.test_linear(a, w, b, passes=passes)
+    assert rel(out, ref) < TOL[passes]
+
+
+def test_linear_exact_small_integers(ctx):
+    """Integer-valued operands are exact in fp16: the GEMM must be bit-exact (catches layout bugs)."""
+    rng = np.random.default_rng(0)
+    a = rng.integers(-4, 5, (256, 192)).astype(np.float32)
+    w = rng.integers(-4, 5, (192, 128)).astype(np.float32)
+    out = ctx.test_linear(a, w, None, passes=1)
+    assert np.array_equal(out, a @ w)
+
+
+CONV_CASES = [
+    # n, cin, H, W, cout, k, stride, upsample
+    (2, 64, 16, 16, 64, 3, 1, 0),
+    (1, 128, 32, 32, 320, 3, 1, 0),
+    (2, 64, 8, 8, 128, 3, 1, 0),
+    (1, 64, 24, 24, 64, 3, 1, 0),
+    (1, 64, 64, 64, 64, 3, 1, 0),
+    (3, 64, 8, 8, 64, 3, 1, 0),
+    (2, 64, 16, 16, 128, 3, 2, 0),
+    (1, 128, 64, 64, 64, 3, 2, 0),
+    (2, 64, 8, 8, 64, 3, 1, 1),
+    (1, 64, 16, 16, 128, 3, 1, 1),
+    (1, 64, 16, 16, 128, 3, 1, 2),
+    (2, 128, 16, 16, 64, 1, 1, 0),
+    (1, 64, 256, 256, 64, 3, 1, 0),
+]
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("n,cin,H,W,cout,k,stride,up", CONV_CASES)
+def test_conv2d(ctx, n, cin, H, W, cout, k, stride, up, passes):
+    x = rnd((n, cin, H, W), 11); w = rnd((cout, cin, k, k), 12, (cin * k * k) ** -0.5); b = rnd((cout,), 13)
+    xt = torch.from_numpy(x).double()
+    if up:
+        xt = F.interpolate(xt, scale_factor=2, mode="nearest")
+    ref = F.conv2d(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double(), stride=stride, padding=k // 2).numpy()
+    out = ctx.test_conv2d(x, w, b, stride=stride, upsample=up, passes=passes)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < TOL[passes]
+
+
+@pytest.mark.parametrize("n,c,H,W", [(2, 320, 16, 16), (1, 64, 8, 8), (2, 960, 8, 8), (1, 128, 64, 64), (1, 1920, 4, 4)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm(ctx, n, c, H, W, silu):
+    x = rnd((n, c, H, W), 21) * 3 + 0.7
+    g = 1 + 0.1 * rnd((c,), 22); b = 0.1 * rnd((c,), 23)
+    ref = F.group_norm(torch.from_numpy(x).double(), 32, torch.from_numpy(g).double(), torch.from_numpy(b).double(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    out = ctx.test_groupnorm(x, g, b, silu)
+    assert rel(out, ref.numpy()) < 5e-6
+
+
+@pytest.mark.parametrize("rows,c", [(100, 320), (64, 640), (33, 1280)])
+def test_layernorm(ctx, rows, c):
+    x = rnd((rows, c), 31) * 2 - 0.3
+    g = 1 + 0.1 * rnd((c,), 32); b = 0.1 * rnd((c,), 33)
+    ref = F.layer_norm(torch.from_numpy(x).double(), (c,), torch.from_numpy(g).double(), torch.from_numpy(b).double(), 1e-5)
+    out = ctx.test_layernorm(x, g, b)
+    assert rel(out, ref.numpy()) < 5e-6
