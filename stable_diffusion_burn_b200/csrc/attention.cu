@@ -1,2 +1,294 @@
-// attention.cu — fused attention (bring-up stub, filled in next)
-#include "common.cuh"
+// attention.cu — fused QK^T . softmax . PV on tcgen05 (flash-style streaming softmax, no N^2 tensor in HBM).
+//
+// Replaces qkv_attention (reference src/model/attention.rs:5-45 == src/backend.rs:88-128, mask = None):
+//   softmax((q d^-1/4)(k d^-1/4)^T) v  ==  softmax(q k^T d^-1/2) v.
+//
+// One CTA = 128 query rows of one (sample, head). Warp roles:
+//   warp 0    : TMA producer — Q once, then K tiles [128 keys][d] and V^T tiles [d][128 keys] per KV step
+//   warp 1    : TMEM allocator + tcgen05.mma issuer: S = Q K^T (fp32 in TMEM), O += P V
+//   warps 2-5 : softmax — one query row per thread: tcgen05.ld S, running max/sum in fp32 (exp2 with the
+//               d^-1/2 scale folded in), lazy O rescale in TMEM, P written as fp16 into 128B-swizzled smem
+// S(j+1) is issued before softmax(j) finishes (the S tile is copied to registers first), so the tensor
+// pipe overlaps the MUFU-bound exponentials.
+#include "attention.cuh"
+
+namespace sdb {
+
+template <int DPAD>
+struct AttnCfg {
+  static constexpr int DC = (DPAD + 63) / 64;           // 64-wide chunks of the head dim
+  static constexpr int ST = DPAD <= 80 ? 2 : 1;          // K/V pipeline stages
+  static constexpr int Q_BYTES = DC * 128 * 128;         // [128 rows][64] x DC, 128 B rows
+  static constexpr int K_BYTES = DC * 128 * 128;
+  static constexpr int V_CHUNK = ((DPAD * 128 + 1023) / 1024) * 1024;  // [DPAD rows][64 keys]
+  static constexpr int V_BYTES = 2 * V_CHUNK;
+  static constexpr int P_BYTES = 2 * 128 * 128;          // [128 rows][128 keys] fp16
+  static constexpr int SMEM = Q_BYTES + ST * (K_BYTES + V_BYTES) + P_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = (128 + DPAD) <= 256 ? 256 : 512;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(192, 1)
+attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                 const __grid_constant__ CUtensorMap mv, const AttnParams p) {
+  using Cfg = AttnCfg<DPAD>;
+  constexpr int DC = Cfg::DC, ST = Cfg::ST;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + ST * Cfg::K_BYTES;
+  uint8_t* sP = sV + ST * Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // ST
+  uint64_t* k_empty = k_full + ST;    // ST
+  uint64_t* v_full = k_empty + ST;    // ST
+  uint64_t* v_empty = v_full + ST;    // ST
+  uint64_t* s_full = v_empty + ST;    // 1
+  uint64_t* s_free = s_full + 1;      // 1 (128 arrivals)
+  uint64_t* p_full = s_free + 1;      // 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 1;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int s = blockIdx.z;
+  const int kvlen = p.kvlen ? p.kvlen[s] : p.Nk;
+  const int T = (kvlen + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mq);
+    tma_prefetch_desc(&mk);
+    tma_prefetch_desc(&mv);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
+  const uint32_t tmem_O = tmem_base + 128;  // DPAD fp32 columns
+
+  if (warp == 0) {
+    // ======================================================================= TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DC; ++c)
+        tma_load_2d(sQ + c * 16384, &mq, q_full, p.q_col0 + h * DPAD + c * 64, s * p.q_rows_per_sample + q0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % ST;
+        const uint32_t ph = (j / ST) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::K_BYTES);
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+          tma_load_2d(sK + st * Cfg::K_BYTES + c * 16384, &mk, &k_full[st], p.k_col0 + h * DPAD + c * 64,
+                      s * p.k_rows_per_sample + j * 128);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], 2 * DPAD * 128);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          tma_load_2d(sV + st * Cfg::V_BYTES + c * Cfg::V_CHUNK, &mv, &v_full[st],
+                      s * p.k_rows_per_sample + j * 128 + c * 64, h * p.d);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, DPAD);
+    auto issue_qk = [&](int j) {
+      const int st = j % ST;
+      mbar_wait(&k_full[st], (j / ST) & 1);
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // softmax has copied S(j-1) out of TMEM
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * Cfg::K_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk) {
+          const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
+          umma_f16(tmem_S, make_sdesc_sw128(qa + off), make_sdesc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_qk(j + 1);
+      const int st = j % ST;
+      mbar_wait(&v_full[st], (j / ST) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * Cfg::V_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t poff = (kk / 4) * 16384 + (kk % 4) * 32;
+          const uint32_t voff = (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
+          umma_f16(tmem_O, make_sdesc_sw128(pa + poff), make_sdesc_sw128(va + voff), idesc_o,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ======================================================================= softmax + epilogue
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_sel = uint32_t(qd * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;  // d^-1/2 * log2(e)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sv[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_sel + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      const int valid = min(128, kvlen - j * 128);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i)
+        if (i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      const float m_new = fmaxf(m_run, mx * sl2);
+      const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O holds PV(j-1); the P buffer is free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, m_new > m_run)) {
+#pragma unroll
+          for (int c = 0; c < DPAD; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_sel + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_sel + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      float sum = 0.f;
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
+        __half2 hp[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i0 = u * 8 + 2 * e;
+          float p0 = (i0 < valid) ? ex2(__uint_as_float(sv[i0]) * sl2 - m_new) : 0.f;
+          float p1 = (i0 + 1 < valid) ? ex2(__uint_as_float(sv[i0 + 1]) * sl2 - m_new) : 0.f;
+          hp[e] = __floats2half2_rn(p0, p1);
+          const float2 pf = __half22float2(hp[e]);  // the row sum uses the values the MMA will see
+          sum += pf.x + pf.y;
+        }
+        const int chunk = u >> 3, uu = u & 7;
+        *reinterpret_cast<uint4*>(prow + chunk * 16384 + ((uu ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(hp);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> fp16 hi(/lo)
+    mbar_wait(pv_done, (T - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int qrow = q0 + r;
+    const bool ok = qrow < p.Nq;
+    const size_t orow = (size_t)(s * p.q_rows_per_sample + qrow) * p.ldo + h * p.d;
+#pragma unroll
+    for (int c = 0; c < DPAD; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_sel + c, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 16; g += 8) {
+        if (ok && c + g < p.d) {
+          __half2 hh[4], hl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float f0 = __uint_as_float(o[g + 2 * e]) * inv_l, f1 = __uint_as_float(o[g + 2 * e + 1]) * inv_l;
+            hh[e] = __floats2half2_rn(f0, f1);
+            const float2 hf = __half22float2(hh[e]);
+            hl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+          }
+          *reinterpret_cast<uint4*>(p.out_hi + orow + c + g) = *reinterpret_cast<uint4*>(hh);
+          if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + orow + c + g) = *reinterpret_cast<uint4*>(hl);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int DPAD>
+static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
+                        cudaStream_t st) {
+  constexpr int smem = AttnCfg<DPAD>::SMEM;
+  static bool attr = false;
+  if (!attr) {
+    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((p.Nq + 127) / 128, p.heads, p.nb);
+  attention_kernel<DPAD><<<grid, 192, smem, st>>>(mq, mk, mv, p);
+  SDB_CUDA(cudaGetLastError());
+}
+
+void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
+                      cudaStream_t st) {
+  switch (p.dpad) {
+    case 48:
+      launch_attn<48>(mq, mk, mv, p, st);
+      break;
+    case 80:
+      launch_attn<80>(mq, mk, mv, p, st);
+      break;
+    case 160:
+      launch_attn<160>(mq, mk, mv, p, st);
+      break;
+    default:
+      throw Error("attention: unsupported head dim " + std::to_string(p.dpad));
+  }
+}
+
+}  // namespace sdb

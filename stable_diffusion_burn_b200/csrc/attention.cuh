@@ -1,0 +1,23 @@
+// attention.cuh — launch descriptor of the fused attention kernel.
+#pragma once
+#include "common.cuh"
+
+namespace sdb {
+
+struct AttnParams {
+  int nb, heads, d, dpad;
+  int Nq, Nk;                 // query rows per sample / maximum key rows per sample
+  int q_rows_per_sample;      // row stride between samples in the Q matrix (and in the output)
+  int k_rows_per_sample;      // row stride between samples in K (= column stride in V^T)
+  int q_col0, k_col0;         // first column of head 0 inside the Q / K matrices
+  const int* kvlen;           // [nb] valid keys per sample, or null (= Nk)
+  float scale;                // d^-1/2
+  __half* out_hi;             // [nb*Nq][ldo], head h at columns h*d
+  __half* out_lo;             // optional residual half
+  int ldo;
+};
+
+void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
+                      cudaStream_t st);
+
+}  // namespace sdb

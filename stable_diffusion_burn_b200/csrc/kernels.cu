@@ -443,11 +443,12 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 // ============================================================ time embedding + GEMV
 // single CTA: t_emb -> lin1 -> silu -> lin2 -> silu(emb) (every consumer applies SiLU first)
 __global__ void __launch_bounds__(1024)
-time_embed_kernel(int t, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+time_embed_kernel(const int* __restrict__ t_dev, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ b2, float* __restrict__ emb_silu) {
   __shared__ float s_t[320];
   __shared__ float s_h[1280];
   const int tid = threadIdx.x;
+  const int t = *t_dev;
   if (tid < 160) {
     // reference unet/mod.rs:24-29: freqs = exp(arange(half) * (-ln(10000)/half)); args = t*freqs; [cos | sin]
     const float f = expf((float)tid * (float)(-9.210340371976184 / 160.0));
@@ -468,7 +469,7 @@ time_embed_kernel(int t, const float* __restrict__ w1, const float* __restrict__
     emb_silu[o] = silu_f(acc);
   }
 }
-void time_embed_launch(int t, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
+void time_embed_launch(const int* t, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
                        cudaStream_t st) {
   time_embed_kernel<<<1, 1024, 0, st>>>(t, w1, b1, w2, b2, emb_silu);
   SDB_CUDA(cudaGetLastError());
@@ -631,13 +632,14 @@ void pack_conv_up2_launch(const float* w, int Cout, int Cin, Half2Ptr out, cudaS
   SDB_CUDA(cudaGetLastError());
 }
 
-__global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out, __half* hi, __half* lo, int row_offset) {
+__global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out, int ldw, int col0, __half* hi, __half* lo,
+                                   int row_offset) {
   // tiled transpose [in][out] -> [out][in]
   __shared__ float tile[32][33];
   const int o0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = i0 + r, o = o0 + threadIdx.x;
-    tile[r][threadIdx.x] = (i < in && o < out) ? w[(size_t)i * out + o] : 0.f;
+    tile[r][threadIdx.x] = (i < in && o < out) ? w[(size_t)i * ldw + col0 + o] : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -645,9 +647,10 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out,
     if (o < out && i < in) split_store1(tile[threadIdx.x][r], hi, lo, (size_t)(row_offset + o) * in + i);
   }
 }
-void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st) {
+void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st, int ldw,
+                        int col0) {
   dim3 grid(ceil_div(out, 32), ceil_div(in, 32)), block(32, 8);
-  pack_linear_kernel<<<grid, block, 0, st>>>(w, in, out, dst.hi, dst.lo, row_offset);
+  pack_linear_kernel<<<grid, block, 0, st>>>(w, in, out, ldw ? ldw : out, col0, dst.hi, dst.lo, row_offset);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -683,6 +686,62 @@ __global__ void pack_small_cout_kernel(const float* __restrict__ w, int Cout, in
 }
 void pack_small_cout_launch(const float* w, int Cout, int Cin, float* out, cudaStream_t st) {
   pack_small_cout_kernel<<<ceil_div(Cout * 9 * Cin, 256), 256, 0, st>>>(w, Cout, Cin, out);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ row softmax (VAE attention, 1 head, d = 512)
+// P[r][:] = softmax(S[r][:] * scale) -> fp16 hi(/lo); one CTA per row, row kept in registers
+template <int PER>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, int cols, float scale_log2, __half* __restrict__ hi,
+                    __half* __restrict__ lo) {
+  __shared__ float red[8];
+  const size_t row = blockIdx.x;
+  const float* sr = S + row * cols;
+  float v[PER];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = threadIdx.x + k * 256;
+    v[k] = i < cols ? sr[i] * scale_log2 : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, red[k]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    v[k] = exp2f(v[k] - mx);
+    sum += v[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += red[k];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < cols) split_store1(v[k] * inv, hi, lo, row * cols + i);
+  }
+}
+void softmax_rows_launch(const float* S, long long rows, int cols, float scale, Half2Ptr out, cudaStream_t st) {
+  const float sl2 = scale * 1.4426950408889634f;
+  if (cols <= 4096)
+    softmax_rows_kernel<16><<<(unsigned)rows, 256, 0, st>>>(S, cols, sl2, out.hi, out.lo);
+  else if (cols <= 9216)
+    softmax_rows_kernel<36><<<(unsigned)rows, 256, 0, st>>>(S, cols, sl2, out.hi, out.lo);
+  else
+    throw Error("softmax_rows: row too long");
   SDB_CUDA(cudaGetLastError());
 }
 

@@ -51,7 +51,7 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 
 // ---- time embedding (reference unet/mod.rs:19-30, 115-118, 718-722)
 // emb = lin2(silu(lin1([cos|sin](t*f)))) ; then for every ResBlock r: e_r = lin_embed_r(silu(emb))
-void time_embed_launch(int t, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
+void time_embed_launch(const int* t_dev, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
                        cudaStream_t st);
 // y[N] = x[K] @ W[K][N] + b  (tiny GEMV, W fp32 [in,out])
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st);
@@ -66,13 +66,18 @@ void scale_launch(const float* x, float s, long long count, float* y, cudaStream
 // N(0,1) latents from a Philox-like counter hash (used only when the caller passes no init latent)
 void randn_launch(float* x, long long count, uint64_t seed, cudaStream_t st);
 
+// ---- row softmax for the 1-head VAE attention: P = softmax(S*scale) rows -> fp16 hi(/lo)
+void softmax_rows_launch(const float* S, long long rows, int cols, float scale, Half2Ptr out, cudaStream_t st);
+
 // ---- weight packing (master fp32 -> kernel layouts)
 // conv OIHW [Cout][Cin][k][k] -> [Cout][k*k*Cin] with K index = tap*Cin + c ; fp16 hi (+lo)
 void pack_conv_launch(const float* w, int Cout, int Cin, int ksize, Half2Ptr out, cudaStream_t st);
 // nearest-2x-upsample folded 3x3 conv: 4 output phases x 2x2 taps, [4][Cout][4*Cin]
 void pack_conv_up2_launch(const float* w, int Cout, int Cin, Half2Ptr out, cudaStream_t st);
 // Linear [in][out] -> [out_row_offset + out][in] inside a packed matrix of row length ld (=in)
-void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st);
+// ldw/col0 select a column slice [col0, col0+out) of a source matrix with row stride ldw (0 -> out)
+void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st, int ldw = 0,
+                        int col0 = 0);
 // GEGLU proj [in][2*H4] -> rows interleaved per 2*half-tile: tile j holds x rows j*half.. then gate rows
 void pack_geglu_launch(const float* w, const float* b, int in, int h4, int half_tile, Half2Ptr dst, float* bias_packed,
                        cudaStream_t st);

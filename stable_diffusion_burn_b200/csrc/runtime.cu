@@ -3,6 +3,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <cmath>
 #include <cstring>
 
 namespace sdb {
@@ -106,10 +107,10 @@ static CUtensorMap make_act_map(const __half* ptr, int C, int W, int H, int P, i
   return m;
 }
 // fp16 matrix [rows][K]; box {64, brows}
-static CUtensorMap make_w_map(const __half* ptr, int K, int rows, int brows) {
+static CUtensorMap make_w_map(const __half* ptr, int K, int rows, int brows, long long ld = 0) {
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : K) * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)brows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
@@ -117,6 +118,38 @@ static CUtensorMap make_w_map(const __half* ptr, int K, int rows, int brows) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weight) failed: " + std::to_string((int)r));
   return m;
+}
+
+// plain fp16 matrix [rows][ld] with a {64, brows} box
+static CUtensorMap make_mat_map(const __half* ptr, long long ld, long long rows, int brows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)brows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(matrix) failed: " + std::to_string((int)r));
+  return m;
+}
+
+void run_attention(Ctx& c, const AttnOp& a) {
+  SDB_CHECK(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0, "attention leading dims must be multiples of 8");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.nb = a.nb, p.heads = a.heads, p.d = a.d, p.dpad = a.dpad, p.Nq = a.Nq, p.Nk = a.Nk;
+  p.q_rows_per_sample = a.q_rows, p.k_rows_per_sample = a.k_rows;
+  p.q_col0 = a.q_col0, p.k_col0 = a.k_col0;
+  p.kvlen = a.kvlen;
+  p.scale = (float)(1.0 / std::sqrt((double)a.d));
+  p.out_hi = a.out.hi, p.out_lo = a.out.lo, p.ldo = a.ldo;
+  const CUtensorMap mq = make_mat_map(a.q, a.ldq, (long long)a.nb * a.q_rows, 128);
+  const CUtensorMap mk = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
+  const CUtensorMap mv = make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
+  const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
+  KernelScope ks(c, KC_ATTN, flops, 0);
+  attention_launch(mq, mk, mv, p, c.stream);
 }
 
 static int pow2_floor(int x) {
@@ -249,9 +282,9 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   for (int phase = 0; phase < phases_out; ++phase) {
     const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
     const __half* wlo = w.p.lo ? w.p.lo + (size_t)phase * w.N * w.K : nullptr;
-    maps.b[0] = make_w_map(whi, w.K, w.N, BN);
+    maps.b[0] = make_w_map(whi, w.K, w.N, BN, w.ld);
     maps.b[1] = maps.b[0];
-    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, w.N, BN);
+    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, w.N, BN, w.ld);
     if (kind == G_CONV3_UP2) {
       const int a = phase >> 1, b = phase & 1;
       p.oa = a, p.ob = b;
@@ -267,7 +300,10 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       p.ws = reinterpret_cast<float*>(c.work.alloc(need));
     }
     {
-      KernelScope ks(c, KC_GEMM, flops, bytes);  // executed FLOPs of this launch (2*M*N*K)
+      // flops = algorithmic 2*M*N*K of this launch; the class' second counter holds the ISSUED tensor-core
+      // FLOPs (x passes for split-fp16 products), not bytes
+      (void)bytes;
+      KernelScope ks(c, KC_GEMM, flops, flops * passes);
       gemm_tc_launch(maps, p, BN, passes, c.stream);
     }
     if (split > 1) {

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "attention.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -60,6 +61,7 @@ struct ActOp {
 struct WeightOp {
   Half2Ptr p;
   int N = 0, K = 0;
+  long long ld = 0;  // row stride in elements (0 -> K)
 };
 enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4 };
 
@@ -113,6 +115,25 @@ void profile_collect(Ctx& c);
 // one tcgen05 GEMM / implicit conv (+ split-K reduction when chosen)
 //   a0 (+a1 = channel concat), geometry kind, weights, passes (1..3), epilogue
 void run_gemm(Ctx& c, int kind, const ActOp& a0, const ActOp* a1, const WeightOp& w, int passes, const Epilogue& ep);
+
+// fused attention over fp16 matrices:
+//   q  [nb*q_rows][ldq]  head h at columns q_col0 + h*dpad (zero padded to dpad)
+//   k  [nb*k_rows][ldk]  head h at columns k_col0 + h*dpad
+//   vT [heads*d][ldv]    sample s at columns s*k_rows
+//   out [nb*q_rows][ldo] head h at columns h*d
+struct AttnOp {
+  const __half* q = nullptr;
+  int ldq = 0, q_col0 = 0, q_rows = 0;
+  const __half* k = nullptr;
+  int ldk = 0, k_col0 = 0, k_rows = 0;
+  const __half* vT = nullptr;
+  int ldv = 0;
+  int nb = 1, heads = 8, d = 0, dpad = 0, Nq = 0, Nk = 0;
+  const int* kvlen = nullptr;
+  Half2Ptr out;
+  int ldo = 0;
+};
+void run_attention(Ctx& c, const AttnOp& a);
 
 const char* kernel_class_name(int cls);
 

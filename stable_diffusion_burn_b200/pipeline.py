@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference's Rust interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as
+  StableDiffusion::{sample_image, sample_latent, latent_to_image}  src/model/stablediffusion/mod.rs:51-160
+  UNet::forward                                                    src/model/unet/mod.rs:109-142
+  Autoencoder::decode_latent                                       src/model/autoencoder/mod.rs:68-71
+Tensors are numpy fp32 arrays with the reference's shapes (NCHW, [n, L, 768]); errors raise
+(the reference panics). No computation happens in Python and there is no fallback path: every call
+goes to libsdb200.so and fails loudly if the CUDA library or a B200 is missing.
+
+Differences forced by the tier (documented in DESIGN.md): the initial latent is an explicit argument
+(the reference draws it from an unseeded backend RNG) and H/W are parameters (the reference hard-codes 64x64).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import Context
+
+
+class UNet:
+    def __init__(self, ctx: Context):
+        self._c = ctx
+
+    def forward(self, x: np.ndarray, timesteps, context: np.ndarray) -> np.ndarray:
+        """x [n,4,H,W]; timesteps Int[1] (one t for the batch); context [n,L,768] -> [n,4,H,W]."""
+        ts = np.asarray(timesteps).reshape(-1)
+        if ts.size != 1:
+            raise ValueError("timesteps must hold exactly one value (reference: Tensor<B,1,Int> of length 1)")
+        return self._c.unet_forward(x, int(ts[0]), context)
+
+
+class Autoencoder:
+    def __init__(self, ctx: Context):
+        self._c = ctx
+
+    def decode_latent(self, latent: np.ndarray) -> np.ndarray:
+        """latent [n,4,H,W] -> image [n,3,8H,8W]."""
+        return self._c.decode_latent(latent)
+
+
+class StableDiffusion:
+    """Owns the device context; `diffusion` and `autoencoder` mirror the reference's fields."""
+
+    def __init__(self, device: int = 0):
+        self.ctx = Context(device)
+        self.diffusion = UNet(self.ctx)
+        self.autoencoder = Autoencoder(self.ctx)
+
+    # ---- weights (reference: load_stable_diffusion / load_record)
+    def init_synthetic(self, seed: int = 0):
+        self.ctx.init_synthetic(seed)
+        self.ctx.finalize_weights()
+        return self
+
+    def load_arrays(self, arrays: dict):
+        for name, a in arrays.items():
+            self.ctx.set_tensor(name, a)
+        self.ctx.finalize_weights()
+        return self
+
+    # ---- hot path
+    def sample_image(self, context, unconditional_context, unconditional_guidance_scale: float, n_steps: int,
+                     init_latent=None, seed: int = 0, height: int = 512, width: int = 512):
+        """-> list of n flat uint8 arrays of H*W*3 (HWC RGB), like the reference's Vec<Vec<u8>>."""
+        rgb = self.ctx.sample_image(context, unconditional_context, unconditional_guidance_scale, n_steps,
+                                    init_latent=init_latent, seed=seed, H=height // 8, W=width // 8)
+        return [rgb[i].reshape(-1) for i in range(rgb.shape[0])]
+
+    def sample_latent(self, context, unconditional_context, unconditional_guidance_scale: float, n_steps: int,
+                      init_latent=None, seed: int = 0, height: int = 512, width: int = 512) -> np.ndarray:
+        return self.ctx.sample_latent(context, unconditional_context, unconditional_guidance_scale, n_steps,
+                                      init_latent=init_latent, seed=seed, H=height // 8, W=width // 8)
+
+    def latent_to_image(self, latent):
+        rgb = self.ctx.latent_to_image(latent)
+        return [rgb[i].reshape(-1) for i in range(rgb.shape[0])]
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,81 @@
+"""Generates tests/golden/*.npz from the CPU oracle (oracle/sd_oracle.py) on the synthetic weights (seed 0).
+
+The reference has no golden vectors for this path and cannot run here (see oracle header: PARITY UNPINNED),
+so these fixtures pin the ORACLE: the CPU suite re-derives a subset and the GPU suite compares the CUDA path
+against them. Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import sd_oracle as O  # noqa: E402
+from stable_diffusion_burn_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.time()
+    P = O.Params(synth.make_params(0))
+    print("params", time.time() - t0, flush=True)
+    with torch.no_grad():
+        # --- UNet known-answer inputs
+        cases = {}
+        # (i) the reference author's eyeball probe: zeros latent, repeat([0.5,1.3],384) context, t=1 (python/dump.py:624-633)
+        x = torch.zeros(1, 4, 64, 64)
+        cases["kat_zeros"] = (x, 1, torch.from_numpy(synth.kat_context()))
+        # (ii) sin ramp latent (python/test_tiny.py:25), L = 13 context, t = 500
+        cases["sin_ramp"] = (torch.from_numpy(synth.sin_ramp((1, 4, 64, 64))), 500, torch.from_numpy(synth.make_context(1, 13)))
+        # (iii) seeded N(0,1) latent, t = 999 (first DDIM step), README-like L = 13
+        cases["randn_t999"] = (torch.from_numpy(synth.make_latent(1, 64, 64)), 999, torch.from_numpy(synth.make_context(1, 13)))
+        # (iv) batch 2, small latent, L = 5
+        cases["batch2_16"] = (torch.from_numpy(synth.make_latent(2, 16, 16, seed=7)), 321, torch.from_numpy(synth.make_context(2, 5, seed=5)))
+        for name, (x, t, ctx) in cases.items():
+            t1 = time.time()
+            taps = {}
+            y = O.unet_forward(P, x, t, ctx, taps=taps)
+            keep = {"out": y.numpy()}
+            for k in ("emb", "input_blocks/conv", "input_blocks/rt1", "input_blocks/d1", "input_blocks/r2", "middle_block",
+                      "output_blocks/ru", "output_blocks/rt7"):
+                v = taps[k].numpy()
+                keep["tap:" + k] = v if v.size <= 70000 else v.reshape(-1)[:: max(1, v.size // 65536)][:65536].copy()
+            np.savez_compressed(os.path.join(OUT, f"unet_{name}.npz"), **keep)
+            print(name, time.time() - t1, "rms", float(y.pow(2).mean().sqrt()), flush=True)
+        # --- VAE decode
+        lat = torch.from_numpy(synth.make_latent(1, 16, 16, seed=21))
+        img = O.decode_latent(P, lat)
+        np.savez_compressed(os.path.join(OUT, "vae_16.npz"), img=img.numpy())
+        lat = torch.from_numpy(synth.make_latent(1, 64, 64, seed=22))
+        t1 = time.time()
+        img = O.decode_latent(P, lat)
+        print("vae64", time.time() - t1, flush=True)
+        np.savez_compressed(os.path.join(OUT, "vae_64.npz"), img_sub=img[:, :, ::8, ::8].numpy().copy(),
+                            img_rows=img[:, :, 250:254, :].numpy().copy(), mean=float(img.mean()), std=float(img.std()))
+        # --- one-step end-to-end (C1 plumbing config): n=1, 64x64, 1 step, cfg 7.5, L = 13, Lu = 2
+        ctx = torch.from_numpy(synth.make_context(1, 13))
+        unc = torch.from_numpy(synth.make_context(1, 2, seed=99))[0]
+        init = torch.from_numpy(synth.make_latent(1, 64, 64))
+        t1 = time.time()
+        lat1 = O.sample_latent(P, ctx, unc, 7.5, 1, init)
+        imgf = O.latent_to_image_f32(P, lat1)
+        u8 = O.to_u8(imgf)
+        print("e2e 1 step", time.time() - t1, flush=True)
+        np.savez_compressed(os.path.join(OUT, "sample_1step.npz"), latent=lat1.numpy(), img_f32_sub=imgf[:, ::4, ::4, :].numpy().copy(),
+                            u8=u8)
+        # --- two DDIM steps on a small latent, batch 2 (exercises alpha_prev lookup and the CFG batch layout)
+        ctx = torch.from_numpy(synth.make_context(2, 7, seed=3))
+        init = torch.from_numpy(synth.make_latent(2, 16, 16, seed=31))
+        lat2 = O.sample_latent(P, ctx, unc, 5.0, 2, init)
+        u8 = O.to_u8(O.latent_to_image_f32(P, lat2))
+        np.savez_compressed(os.path.join(OUT, "sample_2step_b2.npz"), latent=lat2.numpy(), u8=u8)
+    print("done", time.time() - t0)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ def test_synthetic_bit_identical(ctx):
 
 
 def test_set_get_roundtrip(ctx):
-    name, shape, _, _ = topology.all_params()[5]
+    name, shape, _, _ = topology.all_params()[4]  # a 4-D conv weight
     v = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
     ctx.set_tensor(name, v)
     assert np.array_equal(ctx.get_tensor(name, shape), v)
