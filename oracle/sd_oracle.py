@@ -291,24 +291,33 @@ def conv_self_attention_block(P, name, x):
 def decode_latent(P, latent, taps=None, prefix="autoencoder"):
     """reference autoencoder/mod.rs:68-71 + Decoder::forward :204-217 + DecoderBlock :307-324 + Mid :456-463."""
     from stable_diffusion_burn_b200 import topology as T
+    _enter("vae/in")
     x = conv2d(P, f"{prefix}/post_quant_conv", latent.to(P.dtype))
     d = f"{prefix}/decoder"
     x = conv2d(P, f"{d}/conv_in", x, padding=1)
+    _enter("vae/mid1")
     x = resnet_block(P, f"{d}/mid/block_1", x)
+    _enter("vae/attn")
     x = conv_self_attention_block(P, f"{d}/mid/attn", x)
+    _enter("vae/mid2")
     x = resnet_block(P, f"{d}/mid/block_2", x)
     if taps is not None:
         taps["mid"] = x
     nb = len(T.VAE_DECODER_BLOCKS)
     for i in range(nb):
         b = f"{d}/blocks/{i}"
+        _enter(f"vae/b{i}/res1")
         x = resnet_block(P, f"{b}/res1", x)
+        _enter(f"vae/b{i}/res2")
         x = resnet_block(P, f"{b}/res2", x)
+        _enter(f"vae/b{i}/res3")
         x = resnet_block(P, f"{b}/res3", x)
         if i != nb - 1:
+            _enter(f"vae/b{i}/up")
             x = conv2d(P, f"{b}/upsampler", upsample_nearest2x(x), padding=1)
         if taps is not None:
             taps[f"blocks/{i}"] = x
+    _enter("vae/out")
     return conv2d(P, f"{d}/conv_out", silu(group_norm(P, f"{d}/norm_out", x)), padding=1)
 
 

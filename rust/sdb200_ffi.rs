@@ -1,0 +1,115 @@
+//! Reference-side binding of libsdb200.so — SOURCE ONLY (no rustc/cargo in the build image).
+//!
+//! Drop this file into the reference as `src/sdb200.rs`, add `pub mod sdb200;` to `src/lib.rs`, link with
+//! `println!("cargo:rustc-link-lib=dylib=sdb200")` from a build script, and replace the three hot-path calls in
+//! `src/bin/sample/main.rs:100-109`:
+//!
+//!   let images = sd.sample_image(context, unconditional_context, scale, n_steps);
+//! becomes
+//!   let images = sdb200::StableDiffusion::new(0)?.load_dump(&model_name)?
+//!       .sample_image(&context_f32, [n, l], &uncond_f32, lu, scale, n_steps, None, 0)?;
+//!
+//! The signatures keep the reference's argument meaning (src/model/stablediffusion/mod.rs:51-57,
+//! src/model/unet/mod.rs:109-114, src/model/autoencoder/mod.rs:68) with plain fp32 slices in place of
+//! `Tensor<B, D>` (same contiguous row-major contents: NCHW / [n, L, 768]).
+
+use std::ffi::{c_char, c_int, c_void, CStr, CString};
+
+#[repr(C)]
+pub struct SdbCtx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    fn sdb_create(device: c_int, out: *mut *mut SdbCtx) -> c_int;
+    fn sdb_destroy(ctx: *mut SdbCtx) -> c_int;
+    fn sdb_last_error(ctx: *mut SdbCtx) -> *const c_char;
+    fn sdb_set_tensor(ctx: *mut SdbCtx, name: *const c_char, host: *const f32, dims: *const i64, ndim: c_int) -> c_int;
+    fn sdb_finalize_weights(ctx: *mut SdbCtx) -> c_int;
+    fn sdb_unet_forward(ctx: *mut SdbCtx, x: *const f32, timestep: i32, context: *const f32, n: c_int, h: c_int,
+                        w: c_int, l: c_int, out: *mut f32) -> c_int;
+    fn sdb_decode_latent(ctx: *mut SdbCtx, latent: *const f32, n: c_int, h: c_int, w: c_int, img: *mut f32) -> c_int;
+    fn sdb_sample_image(ctx: *mut SdbCtx, context: *const f32, n: c_int, l: c_int, uncond: *const f32, lu: c_int,
+                        guidance_scale: f64, n_steps: c_int, init_latent: *const f32, seed: u64, h: c_int, w: c_int,
+                        rgb: *mut u8) -> c_int;
+    #[allow(dead_code)]
+    fn sdb_sample_image_dev(ctx: *mut SdbCtx, d_context: *const c_void, n: c_int, l: c_int, d_uncond: *const c_void,
+                            lu: c_int, guidance_scale: f64, n_steps: c_int, d_init_latent: *const c_void, h: c_int,
+                            w: c_int, d_rgb: *mut c_void, stream: *mut c_void) -> c_int;
+}
+
+#[derive(Debug)]
+pub struct SdbError(pub String);
+
+pub struct StableDiffusion {
+    ctx: *mut SdbCtx,
+}
+
+impl StableDiffusion {
+    /// Replaces `StableDiffusionConfig::new().init(&device)` (src/model/stablediffusion/mod.rs:22-39).
+    pub fn new(device: i32) -> Result<Self, SdbError> {
+        let mut ctx = std::ptr::null_mut();
+        let rc = unsafe { sdb_create(device, &mut ctx) };
+        if rc != 0 {
+            return Err(SdbError(unsafe { CStr::from_ptr(sdb_last_error(std::ptr::null_mut())) }.to_string_lossy().into()));
+        }
+        Ok(Self { ctx })
+    }
+
+    fn check(&self, rc: c_int) -> Result<(), SdbError> {
+        if rc == 0 {
+            Ok(())
+        } else {
+            Err(SdbError(unsafe { CStr::from_ptr(sdb_last_error(self.ctx)) }.to_string_lossy().into()))
+        }
+    }
+
+    /// Replaces `load_tensor` + `Param::from_tensor` (src/model/load.rs:30-47): `name` is the dump-dir path
+    /// without the `.npy` suffix, e.g. "unet/input_blocks/rt1/res/conv_in/weight".
+    pub fn set_tensor(&self, name: &str, data: &[f32], dims: &[i64]) -> Result<(), SdbError> {
+        let cname = CString::new(name).unwrap();
+        self.check(unsafe { sdb_set_tensor(self.ctx, cname.as_ptr(), data.as_ptr(), dims.as_ptr(), dims.len() as c_int) })
+    }
+
+    pub fn finalize_weights(&self) -> Result<(), SdbError> {
+        self.check(unsafe { sdb_finalize_weights(self.ctx) })
+    }
+
+    /// `UNet::forward(x, timesteps, context)` (src/model/unet/mod.rs:109-114).
+    pub fn unet_forward(&self, x: &[f32], [n, h, w]: [usize; 3], timestep: i32, context: &[f32], l: usize) -> Result<Vec<f32>, SdbError> {
+        let mut out = vec![0f32; n * 4 * h * w];
+        self.check(unsafe {
+            sdb_unet_forward(self.ctx, x.as_ptr(), timestep, context.as_ptr(), n as c_int, h as c_int, w as c_int, l as c_int, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+
+    /// `Autoencoder::decode_latent(latent)` (src/model/autoencoder/mod.rs:68-71).
+    pub fn decode_latent(&self, latent: &[f32], [n, h, w]: [usize; 3]) -> Result<Vec<f32>, SdbError> {
+        let mut img = vec![0f32; n * 3 * 64 * h * w];
+        self.check(unsafe { sdb_decode_latent(self.ctx, latent.as_ptr(), n as c_int, h as c_int, w as c_int, img.as_mut_ptr()) })?;
+        Ok(img)
+    }
+
+    /// `StableDiffusion::sample_image(context, unconditional_context, scale, n_steps) -> Vec<Vec<u8>>`
+    /// (src/model/stablediffusion/mod.rs:51-67). `init_latent = None` draws N(0,1) on the device from `seed`.
+    #[allow(clippy::too_many_arguments)]
+    pub fn sample_image(&self, context: &[f32], [n, l]: [usize; 2], unconditional_context: &[f32], lu: usize,
+                        unconditional_guidance_scale: f64, n_steps: usize, init_latent: Option<&[f32]>, seed: u64)
+                        -> Result<Vec<Vec<u8>>, SdbError> {
+        let (h, w) = (64usize, 64usize); // the reference hard-codes 512x512 (stablediffusion/mod.rs:74-75,116)
+        let mut rgb = vec![0u8; n * 8 * h * 8 * w * 3];
+        self.check(unsafe {
+            sdb_sample_image(self.ctx, context.as_ptr(), n as c_int, l as c_int, unconditional_context.as_ptr(), lu as c_int,
+                             unconditional_guidance_scale, n_steps as c_int,
+                             init_latent.map_or(std::ptr::null(), |s| s.as_ptr()), seed, h as c_int, w as c_int, rgb.as_mut_ptr())
+        })?;
+        Ok(rgb.chunks(8 * h * 8 * w * 3).map(|c| c.to_vec()).collect())
+    }
+}
+
+impl Drop for StableDiffusion {
+    fn drop(&mut self) {
+        unsafe { sdb_destroy(self.ctx) };
+    }
+}

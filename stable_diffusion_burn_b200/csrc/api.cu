@@ -1,6 +1,7 @@
 // api.cu — extern "C" boundary (include/sdb200.h). No exception crosses it.
 #include "../../include/sdb200.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -59,6 +60,7 @@ int sdb_create(int device, sdb_ctx** out) {
                   "; kernels are built for sm_100a only");
     h = new sdb_ctx();
     h->c.device = device;
+    h->c.debug_sync = getenv("SDB_DEBUG_SYNC") && atoi(getenv("SDB_DEBUG_SYNC")) != 0;
     SDB_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
     model_create(h->c);
     *out = h;

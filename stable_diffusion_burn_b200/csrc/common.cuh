@@ -83,9 +83,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if ((++spins & 0x3FF) == 0 && clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
   }
 }
 

@@ -501,20 +501,22 @@ void gemv_launch(const float* x, const float* W, const float* b, int K, int N, f
 
 // ============================================================ sampler elementwise
 __global__ void cfg_ddim_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ lat,
-                                long long count, float scale, float sqrt_1m_at, float inv_sqrt_at, float sqrt_aprev,
+                                long long count, float scale, float sqrt_1m_at, float sqrt_at, float sqrt_aprev,
                                 float dir_coef) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float u = eu[i], c = ec[i];
     const float pred = u + (c - u) * scale;               // stablediffusion/mod.rs:190-191
-    const float x0 = (lat[i] - pred * sqrt_1m_at) * inv_sqrt_at;  // :152
-    lat[i] = x0 * sqrt_aprev + pred * dir_coef;           // :153-155 (sigma = 0)
+    const float x0 = (lat[i] - pred * sqrt_1m_at) / sqrt_at;  // :152
+    const float nl = x0 * sqrt_aprev + pred * dir_coef;   // :153-155 (sigma = 0)
+    lat[i] = nl;
+    lat[i + count] = nl;  // the UNet input batch holds the latent twice (uncond half | cond half)
   }
 }
 void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long long count, float scale,
-                     float sqrt_one_minus_at, float inv_sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st) {
+                     float sqrt_one_minus_at, float sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st) {
   int grid = (int)((count + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  cfg_ddim_kernel<<<grid, 256, 0, st>>>(eps_u, eps_c, latent, count, scale, sqrt_one_minus_at, inv_sqrt_at, sqrt_aprev, dir_coef);
+  cfg_ddim_kernel<<<grid, 256, 0, st>>>(eps_u, eps_c, latent, count, scale, sqrt_one_minus_at, sqrt_at, sqrt_aprev, dir_coef);
   SDB_CUDA(cudaGetLastError());
 }
 

@@ -58,8 +58,9 @@ void gemv_launch(const float* x, const float* W, const float* b, int K, int N, f
 
 // ---- sampler elementwise (reference stablediffusion/mod.rs:152-156, 190-191)
 // pred = u + (c-u)*scale ; x0 = (lat - pred*sqrt(1-a_t))/sqrt(a_t) ; lat' = x0*sqrt(a_prev) + pred*sqrt(1-a_prev)
+// latent holds 2*count floats: the update is written to both halves (uncond | cond inputs of the next step)
 void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long long count, float scale,
-                     float sqrt_one_minus_at, float inv_sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st);
+                     float sqrt_one_minus_at, float sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st);
 // u8 = trunc(clamp((img+1)/2*255, 0, 255)), NCHW fp32 -> NHWC u8 (reference stablediffusion/mod.rs:79-97)
 void to_rgb8_launch(const float* img_nchw, int n, int H, int W, uint8_t* rgb, cudaStream_t st);
 void scale_launch(const float* x, float s, long long count, float* y, cudaStream_t st);

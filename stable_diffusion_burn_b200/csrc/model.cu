@@ -17,12 +17,16 @@
 namespace sdb {
 
 static Model& M(Ctx& c) { return *reinterpret_cast<Model*>(c.model); }
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // tensor-core passes per product as a function of the UNet resolution level (0 = full latent resolution).
 // Budgeted with the oracle's operand-rounding emulation (DESIGN.md "precision"): the two highest-resolution
 // levels carry ~85 % of the fp16 rounding error of a UNet step, so they run the 3-term split product.
 static int g_level_passes[4] = {3, 3, 1, 1};
-static int g_vae_passes = 1;
+// VAE decoder (same emulation study, per block): the latent-resolution stage (mid blocks, attention, first
+// DecoderBlock) and the three upsample convs inject ~63 % of the fp16 rounding error for ~20 % of the FLOPs
+// -> split product there, single pass on the 128^2..512^2 ResnetBlocks.
+static int g_vae_passes_lowres = 3, g_vae_passes_up = 3, g_vae_passes_highres = 1;
 
 // ================================================================================ packing
 static Half2Ptr alloc_half2(Arena& a, size_t count) {
@@ -159,13 +163,13 @@ void model_finalize(Ctx& c) {
   SDB_CUDA(cudaMemcpyAsync(m.emb_b_all, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, c.stream));
   // ---- VAE decoder
   pack_conv(c, m.post_quant), pack_conv(c, m.vae_conv_in), pack_conv(c, m.vae_conv_out);
-  pack_resnet(c, m.mid_block1, g_vae_passes), pack_resnet(c, m.mid_block2, g_vae_passes);
+  pack_resnet(c, m.mid_block1, g_vae_passes_lowres), pack_resnet(c, m.mid_block2, g_vae_passes_lowres);
   pack_norm(c, m.mid_attn.norm);
   pack_conv(c, m.mid_attn.q), pack_conv(c, m.mid_attn.k), pack_conv(c, m.mid_attn.v), pack_conv(c, m.mid_attn.proj_out);
-  m.mid_attn.passes = g_vae_passes;
+  m.mid_attn.passes = g_vae_passes_lowres;
   for (int i = 0; i < 4; ++i) {
-    for (int j = 0; j < 3; ++j) pack_resnet(c, m.dec[i].res[j], g_vae_passes);
-    if (m.dec[i].has_up) pack_conv(c, m.dec[i].up, /*up2=*/true), m.dec[i].up.passes = g_vae_passes;
+    for (int j = 0; j < 3; ++j) pack_resnet(c, m.dec[i].res[j], i == 0 ? g_vae_passes_lowres : g_vae_passes_highres);
+    if (m.dec[i].has_up) pack_conv(c, m.dec[i].up, /*up2=*/true), m.dec[i].up.passes = g_vae_passes_up;
   }
   pack_norm(c, m.vae_norm_out);
   // ---- schedule
@@ -334,11 +338,12 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
     ep.out_f16.hi = qk;
     run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_qk1, P, ep);
   }
-  __half* vT = c.work.get<__half>((size_t)C * Mt);
+  const int Mp = round_up((int)Mt, 32);  // token count padded for the N tiling; pad columns come out zero
+  __half* vT = c.work.get<__half>((size_t)C * Mp);
   {
     // V^T[C][tokens] = Wv^T[C][C] . LN(x)^T : weights as the A operand, tokens as the B operand
     WeightOp tok;
-    tok.p = l16, tok.N = (int)Mt, tok.K = C;
+    tok.p = l16, tok.N = Mp, tok.rows = (int)Mt, tok.K = C;
     Epilogue ep;
     ep.out_f16.hi = vT;
     run_gemm(c, G_LINEAR, f.rows_operand(s.w_v1.p, C, C), nullptr, tok, P, ep);
@@ -347,7 +352,7 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
     AttnOp at;
     at.q = qk, at.ldq = 2 * hd, at.q_col0 = 0, at.q_rows = HW;
     at.k = qk, at.ldk = 2 * hd, at.k_col0 = hd, at.k_rows = HW;
-    at.vT = vT, at.ldv = (int)Mt;
+    at.vT = vT, at.ldv = Mp;
     at.nb = f.nb, at.heads = s.heads, at.d = s.d, at.dpad = s.dpad, at.Nq = HW, at.Nk = HW;
     at.out = o16, at.ldo = C;
     run_attention(c, at);
@@ -578,7 +583,8 @@ static void run_vae_attention(Fwd& f, VaeAttnW& a, const Act& x, Act& out) {
   const int HW = x.H * x.W, C = x.C;
   const long long Mt = (long long)f.nb * HW;
   ActOp h = f.gn_operand(x, nullptr, a.norm, false, lo);
-  Half2Ptr q16 = f.half2((size_t)Mt * C, lo), k16 = f.half2((size_t)Mt * C, lo), vT = f.half2((size_t)C * Mt, lo);
+  const int Mp = round_up((int)Mt, 32);
+  Half2Ptr q16 = f.half2((size_t)Mt * C, lo), k16 = f.half2((size_t)Mt * C, lo), vT = f.half2((size_t)C * Mp, lo);
   Half2Ptr o16 = f.half2((size_t)Mt * C, lo);
   {
     Epilogue ep;
@@ -593,7 +599,7 @@ static void run_vae_attention(Fwd& f, VaeAttnW& a, const Act& x, Act& out) {
   {
     // V^T = Wv . h^T ; the v bias is added after P.V (softmax rows sum to one)
     WeightOp tok;
-    tok.p = h.p, tok.N = (int)Mt, tok.K = C;
+    tok.p = h.p, tok.N = Mp, tok.rows = (int)Mt, tok.K = C;
     Epilogue ep;
     ep.out_f16 = vT;
     run_gemm(c, G_LINEAR, f.rows_operand(a.v.packed.p, C, C), nullptr, tok, P, ep);
@@ -617,7 +623,7 @@ static void run_vae_attention(Fwd& f, VaeAttnW& a, const Act& x, Act& out) {
     }
     WeightOp vs;
     vs.p.hi = vT.hi + (size_t)s * HW, vs.p.lo = vT.lo ? vT.lo + (size_t)s * HW : nullptr;
-    vs.N = C, vs.K = HW, vs.ld = Mt;
+    vs.N = C, vs.K = HW, vs.ld = Mp;
     Epilogue ep;
     ep.out_f16.hi = o16.hi + (size_t)s * HW * C, ep.out_f16.lo = o16.lo ? o16.lo + (size_t)s * HW * C : nullptr;
     ep.bias = a.v.bias;
@@ -709,7 +715,6 @@ struct StreamJoin {  // run on c.stream ordered after / before the caller's stre
     }
   }
 };
-int round_up(int x, int m) { return (x + m - 1) / m * m; }
 }  // namespace
 
 // UNet pass over nb samples with per-sample context lengths. d_ctx_padded [nb][Lpad][768].
@@ -731,6 +736,9 @@ static void unet_pass(Ctx& c, int nb, const float* d_x, const int* d_t, const fl
 void model_unet_forward_dev(Ctx& c, const float* d_x, int t, const float* d_context, int n, int H, int W, int L,
                             float* d_out, cudaStream_t caller) {
   SDB_CHECK(n >= 1 && H % 8 == 0 && W % 8 == 0 && L >= 1, "unet_forward arguments");
+  // the deepest level has (H/8)*(W/8) tokens per sample; TMA tile origins inside the V^T matrix are
+  // per-sample column offsets and must stay 16-byte aligned
+  SDB_CHECK(((H / 8) * (W / 8)) % 8 == 0, "unsupported latent size: (H/8)*(W/8) must be a multiple of 8");
   StreamJoin join(c, caller);
   c.work.reset();
   const int Lpad = round_up(L, 32);
@@ -836,6 +844,7 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
   SDB_CHECK(n >= 1 && L >= 1 && Lu >= 1, "sample arguments");
   SDB_CHECK(n_steps >= 1 && n_steps <= 1000, "n_steps must be in [1,1000] (step_by(0) panics in the reference)");
   SDB_CHECK(H % 8 == 0 && W % 8 == 0, "latent size must be a multiple of 8");
+  SDB_CHECK(((H / 8) * (W / 8)) % 8 == 0, "unsupported latent size: (H/8)*(W/8) must be a multiple of 8");
   StreamJoin join(c, caller);
   c.work.reset();
   const int nb = 2 * n;

@@ -65,6 +65,15 @@ KernelScope::~KernelScope() {
     cudaEventRecord(ev.b, c.stream);
     c.prof.push_back(ev);
   }
+  if (c.debug_sync) {
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "[sdb200] launch #%lld (%s) failed: %s | %s\n", (long long)c.launches, kernel_class_name(cls),
+              cudaGetErrorString(e), c.dbg_label.c_str());
+      fflush(stderr);
+    }
+    c.dbg_label.clear();
+  }
 }
 void profile_collect(Ctx& c) {
   if (c.prof.empty()) return;
@@ -148,6 +157,12 @@ void run_attention(Ctx& c, const AttnOp& a) {
   const CUtensorMap mk = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
   const CUtensorMap mv = make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
   const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
+  if (c.debug_sync) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "attention nb=%d heads=%d d=%d dpad=%d Nq=%d Nk=%d ldq=%d ldk=%d ldv=%d kvlen=%p", a.nb, a.heads,
+             a.d, a.dpad, a.Nq, a.Nk, a.ldq, a.ldk, a.ldv, (const void*)a.kvlen);
+    c.dbg_label = buf;
+  }
   KernelScope ks(c, KC_ATTN, flops, 0);
   attention_launch(mq, mk, mv, p, c.stream);
 }
@@ -246,7 +261,17 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       if (split < 1) split = 1;
     }
   }
+  if (split > 1) {  // no empty K ranges: every split must own at least one iteration
+    const int per = (iters + split - 1) / split;
+    split = (iters + per - 1) / per;
+  }
   p.split_k = split;
+  if (c.debug_sync) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d",
+             kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW);
+    c.dbg_label = buf;
+  }
 
   p.out_f32 = ep.out_f32;
   p.out_f16 = ep.out_f16.hi;
@@ -282,9 +307,10 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   for (int phase = 0; phase < phases_out; ++phase) {
     const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
     const __half* wlo = w.p.lo ? w.p.lo + (size_t)phase * w.N * w.K : nullptr;
-    maps.b[0] = make_w_map(whi, w.K, w.N, BN, w.ld);
+    const int wrows = w.rows ? w.rows : w.N;
+    maps.b[0] = make_w_map(whi, w.K, wrows, BN, w.ld);
     maps.b[1] = maps.b[0];
-    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, w.N, BN, w.ld);
+    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, wrows, BN, w.ld);
     if (kind == G_CONV3_UP2) {
       const int a = phase >> 1, b = phase & 1;
       p.oa = a, p.ob = b;

@@ -62,6 +62,7 @@ struct WeightOp {
   Half2Ptr p;
   int N = 0, K = 0;
   long long ld = 0;  // row stride in elements (0 -> K)
+  int rows = 0;      // rows that really exist (0 -> N); rows in [rows, N) read as zero (TMA OOB fill)
 };
 enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4 };
 
@@ -96,6 +97,9 @@ struct Ctx {
   double cls_ms[KC_COUNT] = {0}, cls_flops[KC_COUNT] = {0}, cls_bytes[KC_COUNT] = {0};
   int64_t cls_launches[KC_COUNT] = {0};
   void* model = nullptr;  // Model* (model.cu)
+  // SDB_DEBUG_SYNC=1: synchronise after every launch and report the failing op (bring-up aid)
+  bool debug_sync = false;
+  std::string dbg_label;
 
   float* master_ptr(const std::string& name);
   const TensorInfo& info(const std::string& name);

@@ -17,6 +17,7 @@ from oracle import sd_oracle as O  # noqa: E402
 from stable_diffusion_burn_b200 import synth  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
+ONLY = set(sys.argv[1:])  # e.g. `make_golden.py batch2_32` regenerates only that UNet case (+ the 2-step sample)
 
 
 def main():
@@ -34,9 +35,11 @@ def main():
         cases["sin_ramp"] = (torch.from_numpy(synth.sin_ramp((1, 4, 64, 64))), 500, torch.from_numpy(synth.make_context(1, 13)))
         # (iii) seeded N(0,1) latent, t = 999 (first DDIM step), README-like L = 13
         cases["randn_t999"] = (torch.from_numpy(synth.make_latent(1, 64, 64)), 999, torch.from_numpy(synth.make_context(1, 13)))
-        # (iv) batch 2, small latent, L = 5
-        cases["batch2_16"] = (torch.from_numpy(synth.make_latent(2, 16, 16, seed=7)), 321, torch.from_numpy(synth.make_context(2, 5, seed=5)))
+        # (iv) batch 2, small latent (32x32 is the smallest size whose deepest level keeps 16-byte aligned tiles), L = 5
+        cases["batch2_32"] = (torch.from_numpy(synth.make_latent(2, 32, 32, seed=7)), 321, torch.from_numpy(synth.make_context(2, 5, seed=5)))
         for name, (x, t, ctx) in cases.items():
+            if ONLY and name not in ONLY:
+                continue
             t1 = time.time()
             taps = {}
             y = O.unet_forward(P, x, t, ctx, taps=taps)
@@ -47,6 +50,8 @@ def main():
                 keep["tap:" + k] = v if v.size <= 70000 else v.reshape(-1)[:: max(1, v.size // 65536)][:65536].copy()
             np.savez_compressed(os.path.join(OUT, f"unet_{name}.npz"), **keep)
             print(name, time.time() - t1, "rms", float(y.pow(2).mean().sqrt()), flush=True)
+        if ONLY and "vae" not in ONLY:
+            return finish(P, t0)
         # --- VAE decode
         lat = torch.from_numpy(synth.make_latent(1, 16, 16, seed=21))
         img = O.decode_latent(P, lat)
@@ -68,12 +73,18 @@ def main():
         print("e2e 1 step", time.time() - t1, flush=True)
         np.savez_compressed(os.path.join(OUT, "sample_1step.npz"), latent=lat1.numpy(), img_f32_sub=imgf[:, ::4, ::4, :].numpy().copy(),
                             u8=u8)
+    finish(P, t0)
+
+
+def finish(P, t0):
+    with torch.no_grad():
         # --- two DDIM steps on a small latent, batch 2 (exercises alpha_prev lookup and the CFG batch layout)
+        unc = torch.from_numpy(synth.make_context(1, 2, seed=99))[0]
         ctx = torch.from_numpy(synth.make_context(2, 7, seed=3))
-        init = torch.from_numpy(synth.make_latent(2, 16, 16, seed=31))
+        init = torch.from_numpy(synth.make_latent(2, 32, 32, seed=31))
         lat2 = O.sample_latent(P, ctx, unc, 5.0, 2, init)
         u8 = O.to_u8(O.latent_to_image_f32(P, lat2))
-        np.savez_compressed(os.path.join(OUT, "sample_2step_b2.npz"), latent=lat2.numpy(), u8=u8)
+        np.savez_compressed(os.path.join(OUT, "sample_2step_b2.npz"), latent=lat2.numpy(), u8=u8[:, ::2, ::2, :].copy())
     print("done", time.time() - t0)
 
 

@@ -69,10 +69,10 @@ def test_u8_cast_truncates_and_clamps():
 
 
 # ------------------------------------------------------------------ oracle vs committed fixtures
-def test_unet_fixture_batch2_16(P):
-    g = np.load(os.path.join(GOLD, "unet_batch2_16.npz"))
+def test_unet_fixture_batch2_32(P):
+    g = np.load(os.path.join(GOLD, "unet_batch2_32.npz"))
     with torch.no_grad():
-        y = O.unet_forward(P, torch.from_numpy(synth.make_latent(2, 16, 16, seed=7)), 321, torch.from_numpy(synth.make_context(2, 5, seed=5)))
+        y = O.unet_forward(P, torch.from_numpy(synth.make_latent(2, 32, 32, seed=7)), 321, torch.from_numpy(synth.make_context(2, 5, seed=5)))
     assert np.allclose(y.numpy(), g["out"], rtol=0, atol=2e-5 * np.abs(g["out"]).max())
 
 
