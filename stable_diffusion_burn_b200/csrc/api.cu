@@ -358,12 +358,14 @@ int sdb_test_groupnorm(sdb_ctx* ctx, const float* x, const float* gamma, const f
   float* d_g = c.work.get<float>(ch);
   float* d_b = c.work.get<float>(ch);
   double* d_s = c.work.get<double>((size_t)n * 64);
+  unsigned int* d_t = c.work.get<unsigned int>(n);
+  float* d_p = c.work.get<float>(gn_stats_partial_floats(n, H * W));
   SDB_CUDA(cudaMemcpyAsync(d_x, x, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
   SDB_CUDA(cudaMemcpyAsync(d_g, gamma, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
   SDB_CUDA(cudaMemcpyAsync(d_b, beta, sizeof(float) * ch, cudaMemcpyHostToDevice, c.stream));
-  SDB_CUDA(cudaMemsetAsync(d_s, 0, sizeof(double) * n * 64, c.stream));
+  SDB_CUDA(cudaMemsetAsync(d_t, 0, sizeof(unsigned int) * n, c.stream));
   nchw_to_nhwc_launch(d_x, n, ch, H, W, d_xh, c.stream);
-  gn_stats_launch(d_xh, ch, nullptr, 0, n, H * W, d_s, c.stream);
+  gn_stats_launch(d_xh, ch, nullptr, 0, n, H * W, d_s, d_p, d_t, c.stream);
   gn_apply_f32_launch(d_xh, ch, n, H * W, silu, d_s, d_g, d_b, 1e-5f, d_yh, c.stream);
   nhwc_to_nchw_launch(d_yh, n, ch, H, W, d_y, c.stream);
   SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * cnt, cudaMemcpyDeviceToHost, c.stream));

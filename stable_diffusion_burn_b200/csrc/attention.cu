@@ -3,28 +3,34 @@
 // Replaces qkv_attention (reference src/model/attention.rs:5-45 == src/backend.rs:88-128, mask = None):
 //   softmax((q d^-1/4)(k d^-1/4)^T) v  ==  softmax(q k^T d^-1/2) v.
 //
-// One CTA = 128 query rows of one (sample, head). Warp roles:
-//   warp 0    : TMA producer — Q once, then K tiles [128 keys][d] and V^T tiles [d][128 keys] per KV step
-//   warp 1    : TMEM allocator + tcgen05.mma issuer: S = Q K^T (fp32 in TMEM), O += P V
-//   warps 2-5 : softmax — one query row per thread: tcgen05.ld S, running max/sum in fp32 (exp2 with the
-//               d^-1/2 scale folded in), lazy O rescale in TMEM, P written as fp16 into 128B-swizzled smem
-// S(j+1) is issued before softmax(j) finishes (the S tile is copied to registers first), so the tensor
-// pipe overlaps the MUFU-bound exponentials.
+// One CTA = NG x 128 query rows of one (sample, head); NG = 2 query tiles ping-pong on one K/V stream
+// (while the softmax warps of tile 0 run their exponentials, the tensor pipe works for tile 1, and the K/V
+// tiles are fetched from L2 once for 256 query rows). Warp roles:
+//   warp 0          : TMA producer — Q tiles once, then K tiles [128 keys][d] and V^T tiles [d][128 keys]
+//   warp 1          : TMEM allocator + tcgen05.mma issuer: S_g = Q_g K^T (fp32 in TMEM), O_g += P_g V
+//   warps 2..2+4*NG : softmax groups — one query row per thread: tcgen05.ld S, running max/sum in fp32
+//                     (exp2 with the d^-1/2 scale folded in), lazy O rescale in TMEM, P written as fp16
+//                     into 128B-swizzled smem
+// S_g(j+1) is issued as soon as the group has copied S_g(j) to registers, so QK^T overlaps the exponentials.
 #include "attention.cuh"
 
 namespace sdb {
 
-template <int DPAD>
+template <int DPAD, int NG>
 struct AttnCfg {
-  static constexpr int DC = (DPAD + 63) / 64;           // 64-wide chunks of the head dim
-  static constexpr int ST = DPAD <= 80 ? 2 : 1;          // K/V pipeline stages
-  static constexpr int Q_BYTES = DC * 128 * 128;         // [128 rows][64] x DC, 128 B rows
+  static constexpr int DC = (DPAD + 63) / 64;                          // 64-wide chunks of the head dim
+  static constexpr int Q_TILE = DC * 128 * 128;                         // [128 rows][64] x DC, 128 B rows
   static constexpr int K_BYTES = DC * 128 * 128;
-  static constexpr int V_CHUNK = ((DPAD * 128 + 1023) / 1024) * 1024;  // [DPAD rows][64 keys]
+  static constexpr int V_CHUNK = ((DPAD * 128 + 1023) / 1024) * 1024;   // [DPAD rows][64 keys]
   static constexpr int V_BYTES = 2 * V_CHUNK;
-  static constexpr int P_BYTES = 2 * 128 * 128;          // [128 rows][128 keys] fp16
-  static constexpr int SMEM = Q_BYTES + ST * (K_BYTES + V_BYTES) + P_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = (128 + DPAD) <= 256 ? 256 : 512;
+  static constexpr int P_TILE = 2 * 128 * 128;                          // [128 rows][128 keys] fp16
+  static constexpr int FIXED = NG * (Q_TILE + P_TILE) + 512 + 1024;
+  static constexpr int ST = (FIXED + 2 * (K_BYTES + V_BYTES) <= 225 * 1024) ? 2 : 1;  // K/V pipeline stages
+  static constexpr int SMEM = FIXED + ST * (K_BYTES + V_BYTES);
+  static constexpr int TMEM_NEED = NG * (128 + DPAD);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(TMEM_NEED <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "smem budget");
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -33,32 +39,32 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int DPAD>
-__global__ void __launch_bounds__(192, 1)
+template <int DPAD, int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const AttnParams p) {
-  using Cfg = AttnCfg<DPAD>;
+  using Cfg = AttnCfg<DPAD, NG>;
   constexpr int DC = Cfg::DC, ST = Cfg::ST;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::Q_BYTES;
-  uint8_t* sV = sK + ST * Cfg::K_BYTES;
-  uint8_t* sP = sV + ST * Cfg::V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // ST
-  uint64_t* k_empty = k_full + ST;    // ST
-  uint64_t* v_full = k_empty + ST;    // ST
-  uint64_t* v_empty = v_full + ST;    // ST
-  uint64_t* s_full = v_empty + ST;    // 1
-  uint64_t* s_free = s_full + 1;      // 1 (128 arrivals)
-  uint64_t* p_full = s_free + 1;      // 1 (128 arrivals)
-  uint64_t* pv_done = p_full + 1;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint8_t* sQ = smem;                              // NG tiles
+  uint8_t* sP = sQ + NG * Cfg::Q_TILE;             // NG tiles
+  uint8_t* sK = sP + NG * Cfg::P_TILE;             // ST stages
+  uint8_t* sV = sK + ST * Cfg::K_BYTES;            // ST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * Cfg::V_BYTES);
+  uint64_t* q_full = bars;             // 1
+  uint64_t* k_full = q_full + 1;       // ST
+  uint64_t* k_empty = k_full + ST;     // ST
+  uint64_t* v_full = k_empty + ST;     // ST
+  uint64_t* v_empty = v_full + ST;     // ST
+  uint64_t* s_full = v_empty + ST;     // NG
+  uint64_t* s_free = s_full + NG;      // NG (128 arrivals each)
+  uint64_t* p_full = s_free + NG;      // NG (128 arrivals each)
+  uint64_t* pv_done = p_full + NG;     // NG
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
+  const int q0 = blockIdx.x * (128 * NG);
   const int h = blockIdx.y;
   const int s = blockIdx.z;
   const int kvlen = p.kvlen ? p.kvlen[s] : p.Nk;
@@ -72,10 +78,12 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&pv_done[g], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -91,16 +99,18 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
-  const uint32_t tmem_O = tmem_base + 128;  // DPAD fp32 columns
+  // columns: S_g at g*128 ; O_g at NG*128 + g*DPAD
 
   if (warp == 0) {
     // ======================================================================= TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      mbar_expect_tx(q_full, NG * Cfg::Q_TILE);
 #pragma unroll
-      for (int c = 0; c < DC; ++c)
-        tma_load_2d(sQ + c * 16384, &mq, q_full, p.q_col0 + h * DPAD + c * 64, s * p.q_rows_per_sample + q0);
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int c = 0; c < DC; ++c)
+          tma_load_2d(sQ + g * Cfg::Q_TILE + c * 16384, &mq, q_full, p.q_col0 + h * DPAD + c * 64,
+                      s * p.q_rows_per_sample + q0 + g * 128);
       for (int j = 0; j < T; ++j) {
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
@@ -122,94 +132,108 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     // ======================================================================= MMA issuer
     constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
     constexpr uint32_t idesc_o = make_idesc_f16(128, DPAD);
-    auto issue_qk = [&](int j) {
+    auto issue_qk = [&](int g, int j) {
       const int st = j % ST;
-      mbar_wait(&k_full[st], (j / ST) & 1);
-      if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // softmax has copied S(j-1) out of TMEM
+      if (g == 0) mbar_wait(&k_full[st], (j / ST) & 1);
+      if (j > 0) mbar_wait(&s_free[g], (j - 1) & 1);  // group g has copied S_g(j-1) out of TMEM
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * Cfg::K_BYTES);
+        const uint32_t qa = smem_u32(sQ + g * Cfg::Q_TILE), ka = smem_u32(sK + st * Cfg::K_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk) {
           const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
-          umma_f16(tmem_S, make_sdesc_sw128(qa + off), make_sdesc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+          umma_f16(tmem_base + g * 128, make_sdesc_sw128(qa + off), make_sdesc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+        if (g == NG - 1) umma_commit(&k_empty[st]);  // the K stage is free once the last group's QK retires
+        umma_commit(&s_full[g]);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
-    issue_qk(0);
+    for (int g = 0; g < NG; ++g) issue_qk(g, 0);
     for (int j = 0; j < T; ++j) {
-      if (j + 1 < T) issue_qk(j + 1);
       const int st = j % ST;
-      mbar_wait(&v_full[st], (j / ST) & 1);
-      mbar_wait(p_full, j & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * Cfg::V_BYTES);
+      for (int g = 0; g < NG; ++g) {
+        if (g == 0) mbar_wait(&v_full[st], (j / ST) & 1);
+        mbar_wait(&p_full[g], j & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t pa = smem_u32(sP + g * Cfg::P_TILE), va = smem_u32(sV + st * Cfg::V_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t poff = (kk / 4) * 16384 + (kk % 4) * 32;
-          const uint32_t voff = (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
-          umma_f16(tmem_O, make_sdesc_sw128(pa + poff), make_sdesc_sw128(va + voff), idesc_o,
-                   (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t poff = (kk / 4) * 16384 + (kk % 4) * 32;
+            const uint32_t voff = (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
+            umma_f16(tmem_base + NG * 128 + g * DPAD, make_sdesc_sw128(pa + poff), make_sdesc_sw128(va + voff), idesc_o,
+                     (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          if (g == NG - 1) umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[g]);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+        __syncwarp();
+        if (j + 1 < T) issue_qk(g, j + 1);
       }
-      __syncwarp();
     }
   } else {
-    // ======================================================================= softmax + epilogue
+    // ======================================================================= softmax groups + epilogue
+    const int g = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_sel = uint32_t(qd * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_sel;
+    const uint32_t tO = tmem_base + NG * 128 + g * DPAD + lane_sel;
+    uint8_t* prow = sP + g * Cfg::P_TILE + r * 128;
     const float sl2 = p.scale * 1.4426950408889634f;  // d^-1/2 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < T; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
       uint32_t sv[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_S + lane_sel + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);
+      mbar_arrive(&s_free[g]);
       const int valid = min(128, kvlen - j * 128);
       float mx = -INFINITY;
+      if (valid == 128) {
 #pragma unroll
-      for (int i = 0; i < 128; ++i)
-        if (i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      }
       const float m_new = fmaxf(m_run, mx * sl2);
       const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // O holds PV(j-1); the P buffer is free again
+        mbar_wait(&pv_done[g], (j - 1) & 1);  // O_g holds PV(j-1); the P buffer is free again
         tc_fence_after();
         if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
           for (int c = 0; c < DPAD; c += 16) {
             uint32_t o[16];
-            tmem_ld16(tmem_O + lane_sel + c, o);
+            tmem_ld16(tO + c, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem_O + lane_sel + c, o);
+            tmem_st16(tO + c, o);
           }
           tmem_st_wait();
         }
       }
       float sum = 0.f;
-      uint8_t* prow = sP + r * 128;
 #pragma unroll
       for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
         __half2 hp[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i0 = u * 8 + 2 * e;
-          float p0 = (i0 < valid) ? ex2(__uint_as_float(sv[i0]) * sl2 - m_new) : 0.f;
-          float p1 = (i0 + 1 < valid) ? ex2(__uint_as_float(sv[i0 + 1]) * sl2 - m_new) : 0.f;
+          float p0 = ex2(fmaf(__uint_as_float(sv[i0]), sl2, -m_new));
+          float p1 = ex2(fmaf(__uint_as_float(sv[i0 + 1]), sl2, -m_new));
+          if (valid != 128) {
+            p0 = (i0 < valid) ? p0 : 0.f;
+            p1 = (i0 + 1 < valid) ? p1 : 0.f;
+          }
           hp[e] = __floats2half2_rn(p0, p1);
           const float2 pf = __half22float2(hp[e]);  // the row sum uses the values the MMA will see
           sum += pf.x + pf.y;
@@ -221,33 +245,33 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       m_run = m_new;
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[g]);
     }
     // ---- epilogue: O / l -> fp16 hi(/lo)
-    mbar_wait(pv_done, (T - 1) & 1);
+    mbar_wait(&pv_done[g], (T - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
-    const int qrow = q0 + r;
+    const int qrow = q0 + g * 128 + r;
     const bool ok = qrow < p.Nq;
     const size_t orow = (size_t)(s * p.q_rows_per_sample + qrow) * p.ldo + h * p.d;
 #pragma unroll
     for (int c = 0; c < DPAD; c += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_O + lane_sel + c, o);
+      tmem_ld16(tO + c, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 16; g += 8) {
-        if (ok && c + g < p.d) {
+      for (int gg = 0; gg < 16; gg += 8) {
+        if (ok && c + gg < p.d) {
           __half2 hh[4], hl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float f0 = __uint_as_float(o[g + 2 * e]) * inv_l, f1 = __uint_as_float(o[g + 2 * e + 1]) * inv_l;
+            const float f0 = __uint_as_float(o[gg + 2 * e]) * inv_l, f1 = __uint_as_float(o[gg + 2 * e + 1]) * inv_l;
             hh[e] = __floats2half2_rn(f0, f1);
             const float2 hf = __half22float2(hh[e]);
             hl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
           }
-          *reinterpret_cast<uint4*>(p.out_hi + orow + c + g) = *reinterpret_cast<uint4*>(hh);
-          if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + orow + c + g) = *reinterpret_cast<uint4*>(hl);
+          *reinterpret_cast<uint4*>(p.out_hi + orow + c + gg) = *reinterpret_cast<uint4*>(hh);
+          if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + orow + c + gg) = *reinterpret_cast<uint4*>(hl);
         }
       }
     }
@@ -260,31 +284,32 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   }
 }
 
-template <int DPAD>
+template <int DPAD, int NG>
 static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
                         cudaStream_t st) {
-  constexpr int smem = AttnCfg<DPAD>::SMEM;
+  constexpr int smem = AttnCfg<DPAD, NG>::SMEM;
   static bool attr = false;
   if (!attr) {
-    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  dim3 grid((p.Nq + 127) / 128, p.heads, p.nb);
-  attention_kernel<DPAD><<<grid, 192, smem, st>>>(mq, mk, mv, p);
+  dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
+  attention_kernel<DPAD, NG><<<grid, 64 + 128 * NG, smem, st>>>(mq, mk, mv, p);
   SDB_CUDA(cudaGetLastError());
 }
 
 void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
                       cudaStream_t st) {
+  const bool two = p.Nq > 128;  // two ping-pong query tiles per CTA when there are at least two tiles of rows
   switch (p.dpad) {
     case 48:
-      launch_attn<48>(mq, mk, mv, p, st);
+      two ? launch_attn<48, 2>(mq, mk, mv, p, st) : launch_attn<48, 1>(mq, mk, mv, p, st);
       break;
     case 80:
-      launch_attn<80>(mq, mk, mv, p, st);
+      two ? launch_attn<80, 2>(mq, mk, mv, p, st) : launch_attn<80, 1>(mq, mk, mv, p, st);
       break;
     case 160:
-      launch_attn<160>(mq, mk, mv, p, st);
+      launch_attn<160, 1>(mq, mk, mv, p, st);
       break;
     default:
       throw Error("attention: unsupported head dim " + std::to_string(p.dpad));

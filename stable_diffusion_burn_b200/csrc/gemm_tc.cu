@@ -184,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             float x1 = __uint_as_float(vx[j + 1]) + p.bias[col0 + c + j + 1];
             float g0 = __uint_as_float(vg[j]) + p.bias[col0 + HB + c + j];
             float g1 = __uint_as_float(vg[j + 1]) + p.bias[col0 + HB + c + j + 1];
-            float y0 = x0 * gelu_erf_f(g0), y1 = x1 * gelu_erf_f(g1);
+            float y0 = x0 * gelu_erf_fast(g0), y1 = x1 * gelu_erf_fast(g1);
             __half2 h = __floats2half2_rn(y0, y1);
             *reinterpret_cast<__half2*>(o + j) = h;
             if (ol) {

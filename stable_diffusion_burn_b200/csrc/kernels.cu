@@ -25,16 +25,18 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __half* hi, __
 }
 
 // ============================================================ GroupNorm statistics
+// Deterministic two-level reduction (no floating-point atomics): every CTA reduces its pixel chunk per group in a
+// fixed order and writes a partial; the last CTA of an image (ticket counter) folds the partials in chunk order.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x0, int C0,
                                                        const float* __restrict__ x1, int C1, int HW, int pix_per_cta,
-                                                       double* __restrict__ sums) {
-  __shared__ float s_sum[32], s_sq[32];
+                                                       double* __restrict__ sums, float* __restrict__ partials,
+                                                       unsigned int* __restrict__ tickets) {
+  __shared__ float s_pair[2][1280];  // per channel-pair (sum, sumsq), C <= 2560
+  __shared__ bool s_last;
   const int n = blockIdx.y;
   const int C = C0 + C1, gs = C / 32;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  if (threadIdx.x < 32) s_sum[threadIdx.x] = 0.f, s_sq[threadIdx.x] = 0.f;
-  __syncthreads();
   for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
     const int c = cp * 2;
     const float* ptr;
@@ -62,23 +64,43 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
       s += v.x + v.y;
       q += v.x * v.x + v.y * v.y;
     }
-    const int g = c / gs;
-    atomicAdd(&s_sum[g], s);
-    atomicAdd(&s_sq[g], q);
+    s_pair[0][cp] = s;
+    s_pair[1][cp] = q;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    atomicAdd(&sums[((size_t)n * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
-    atomicAdd(&sums[((size_t)n * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  const int chunks = gridDim.x;
+  if (threadIdx.x < 64) {  // thread = (group, stat): fold the group's channel pairs in index order
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int pairs = gs / 2;
+    float acc = 0.f;
+    for (int i = 0; i < pairs; ++i) acc += s_pair[which][g * pairs + i];
+    partials[((size_t)n * chunks + blockIdx.x) * 64 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1u) == (unsigned)(chunks - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < 64) {
+    __threadfence();
+    double acc = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) acc += (double)partials[((size_t)n * chunks + ch) * 64 + threadIdx.x];
+    sums[(size_t)n * 64 + threadIdx.x] = acc;  // [n][32][2]
   }
 }
 
-void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, cudaStream_t st) {
-  SDB_CHECK((C0 + C1) % 64 == 0 && C0 % 2 == 0, "GroupNorm channels");
+size_t gn_stats_partial_floats(int n, int HW) {
+  int pix = (int)((((long long)HW * n) + 591) / 592);
+  if (pix < 16) pix = 16;
+  return (size_t)n * ceil_div(HW, pix) * 64;
+}
+
+void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, float* partials,
+                     unsigned int* tickets, cudaStream_t st) {
+  SDB_CHECK((C0 + C1) % 64 == 0 && C0 % 2 == 0 && C0 + C1 <= 2560, "GroupNorm channels");
   int pix = (int)((((long long)HW * n) + 591) / 592);
   if (pix < 16) pix = 16;
   dim3 grid(ceil_div(HW, pix), n);
-  gn_stats_kernel<<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, pix, sums);
+  gn_stats_kernel<<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, pix, sums, partials, tickets);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -441,61 +463,50 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 }
 
 // ============================================================ time embedding + GEMV
-// single CTA: t_emb -> lin1 -> silu -> lin2 -> silu(emb) (every consumer applies SiLU first)
-__global__ void __launch_bounds__(1024)
-time_embed_kernel(const int* __restrict__ t_dev, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                  const float* __restrict__ b2, float* __restrict__ emb_silu) {
-  __shared__ float s_t[320];
-  __shared__ float s_h[1280];
-  const int tid = threadIdx.x;
-  const int t = *t_dev;
-  if (tid < 160) {
-    // reference unet/mod.rs:24-29: freqs = exp(arange(half) * (-ln(10000)/half)); args = t*freqs; [cos | sin]
-    const float f = expf((float)tid * (float)(-9.210340371976184 / 160.0));
-    const float a = (float)t * f;
-    s_t[tid] = cosf(a);
-    s_t[160 + tid] = sinf(a);
-  }
-  __syncthreads();
-  for (int o = tid; o < 1280; o += blockDim.x) {
-    float acc = b1[o];
-    for (int k = 0; k < 320; ++k) acc += s_t[k] * w1[(size_t)k * 1280 + o];
-    s_h[o] = silu_f(acc);
-  }
-  __syncthreads();
-  for (int o = tid; o < 1280; o += blockDim.x) {
-    float acc = b2[o];
-    for (int k = 0; k < 1280; ++k) acc += s_h[k] * w2[(size_t)k * 1280 + o];
-    emb_silu[o] = silu_f(acc);
-  }
-}
-void time_embed_launch(const int* t, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
-                       cudaStream_t st) {
-  time_embed_kernel<<<1, 1024, 0, st>>>(t, w1, b1, w2, b2, emb_silu);
-  SDB_CUDA(cudaGetLastError());
-}
-
-// y[N] = x[K] W[K][N] + b ; block handles 128 outputs, 8 k-slices reduced through smem
+// y[N] = act(x[K] W[K][N] + b); a block owns 32 outputs, 8 k-slices reduced through smem.
+// t_dev != null: x is the sinusoidal timestep embedding (reference unet/mod.rs:24-29), K must be 320.
 __global__ void __launch_bounds__(256)
-gemv_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b, int K, int N,
-            float* __restrict__ y) {
+gemv_kernel(const float* __restrict__ x, const int* __restrict__ t_dev, const float* __restrict__ W,
+            const float* __restrict__ b, int K, int N, int silu, float* __restrict__ y) {
   __shared__ float s_part[8][32];
+  __shared__ float s_x[1280];
+  if (t_dev) {
+    const int t = *t_dev;
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+      // freqs = exp(arange(half) * (-ln(10000)/half)); args = t*freqs; [cos | sin]
+      const float f = expf((float)i * (float)(-9.210340371976184 / 160.0));
+      const float a = (float)t * f;
+      s_x[i] = cosf(a);
+      s_x[160 + i] = sinf(a);
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_x[i] = x[i];
+  }
+  __syncthreads();
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ks = threadIdx.x >> 5;  // 0..7
   float acc = 0.f;
   if (col < N)
-    for (int k = ks; k < K; k += 8) acc += x[k] * W[(size_t)k * N + col];
+    for (int k = ks; k < K; k += 8) acc += s_x[k] * W[(size_t)k * N + col];
   s_part[ks][threadIdx.x & 31] = acc;
   __syncthreads();
   if (ks == 0 && col < N) {
     float s = b ? b[col] : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += s_part[j][threadIdx.x & 31];
-    y[col] = s;
+    y[col] = silu ? silu_f(s) : s;
   }
 }
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st) {
-  gemv_kernel<<<ceil_div(N, 32), 256, 0, st>>>(x, W, b, K, N, y);
+  SDB_CHECK(K <= 1280, "gemv K");
+  gemv_kernel<<<ceil_div(N, 32), 256, 0, st>>>(x, nullptr, W, b, K, N, 0, y);
+  SDB_CUDA(cudaGetLastError());
+}
+// emb_silu = silu(lin2(silu(lin1(timestep_embedding(t)))))  — two multi-CTA GEMVs (was one CTA: 140 us)
+void time_embed_launch(const int* t, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
+                       float* emb_silu, cudaStream_t st) {
+  gemv_kernel<<<ceil_div(1280, 32), 256, 0, st>>>(nullptr, t, w1, b1, 320, 1280, 1, hidden);
+  gemv_kernel<<<ceil_div(1280, 32), 256, 0, st>>>(hidden, nullptr, w2, b2, 1280, 1280, 1, emb_silu);
   SDB_CUDA(cudaGetLastError());
 }
 

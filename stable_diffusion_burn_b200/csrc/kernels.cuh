@@ -12,9 +12,11 @@ struct Half2Ptr {
 };
 
 // ---- GroupNorm (reference src/model/groupnorm/mod.rs:53-82), NHWC fp32, optional 2-source concat
-// sums: [n][32][2] doubles (sum, sum of squares), must be zero before the call
-void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums,
-                     cudaStream_t st);
+// sums: [n][32][2] doubles (sum, sum of squares). Deterministic: per-CTA partials (scratch `partials`,
+// gn_stats_partial_floats(n,HW) floats) folded in fixed order by the last CTA; `tickets` [n] must be zero.
+size_t gn_stats_partial_floats(int n, int HW);
+void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, float* partials,
+                     unsigned int* tickets, cudaStream_t st);
 // mode bits
 enum : int { PREP_NORM = 1, PREP_SILU = 2, PREP_UP2 = 4, PREP_PHASE2 = 8 };
 // Stages a conv/GEMM A operand: y = [silu]([groupnorm](cat(x0,x1))) -> fp16 hi(/lo).
@@ -51,8 +53,8 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 
 // ---- time embedding (reference unet/mod.rs:19-30, 115-118, 718-722)
 // emb = lin2(silu(lin1([cos|sin](t*f)))) ; then for every ResBlock r: e_r = lin_embed_r(silu(emb))
-void time_embed_launch(const int* t_dev, const float* w1, const float* b1, const float* w2, const float* b2, float* emb_silu,
-                       cudaStream_t st);
+void time_embed_launch(const int* t_dev, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
+                       float* emb_silu, cudaStream_t st);
 // y[N] = x[K] @ W[K][N] + b  (tiny GEMV, W fp32 [in,out])
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st);
 

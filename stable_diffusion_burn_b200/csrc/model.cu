@@ -197,16 +197,25 @@ struct Fwd {
   Model& m;
   int nb;
   double* gn_sums = nullptr;  // [slots][nb][32][2]
+  unsigned int* gn_tickets = nullptr;  // [slots][nb]
   int gn_slot = 0, gn_slots = 0;
   Fwd(Ctx& c_, int nb_) : c(c_), m(M(c_)), nb(nb_) {}
   void init_sums(int slots) {
     gn_slots = slots;
     gn_sums = c.work.get<double>((size_t)slots * nb * 64);
-    SDB_CUDA(cudaMemsetAsync(gn_sums, 0, sizeof(double) * slots * nb * 64, c.stream));
+    gn_tickets = c.work.get<unsigned int>((size_t)slots * nb);
+    SDB_CUDA(cudaMemsetAsync(gn_tickets, 0, sizeof(unsigned int) * slots * nb, c.stream));
   }
-  double* next_sums() {
+  // GroupNorm statistics of cat(x0,x1): returns the [nb][32][2] sums
+  double* stats(const float* x0, int C0, const float* x1, int C1, int HW) {
     SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
-    return gn_sums + (size_t)(gn_slot++) * nb * 64;
+    double* sums = gn_sums + (size_t)gn_slot * nb * 64;
+    unsigned int* tk = gn_tickets + (size_t)gn_slot * nb;
+    gn_slot++;
+    float* part = c.work.get<float>(gn_stats_partial_floats(nb, HW));
+    KernelScope ks(c, KC_GN_STATS, 0, (double)nb * HW * (C0 + C1) * 4.0);
+    gn_stats_launch(x0, C0, x1, C1, nb, HW, sums, part, tk, c.stream);
+    return sums;
   }
   Act act(int H, int W, int C) {
     Act a;
@@ -223,11 +232,7 @@ struct Fwd {
   // GroupNorm(+SiLU) of cat(x0,x1) staged as an fp16 operand
   ActOp gn_operand(const Act& x0, const Act* x1, const NormW& nw, bool silu, bool lo) {
     const int C = x0.C + (x1 ? x1->C : 0);
-    double* sums = next_sums();
-    {
-      KernelScope ks(c, KC_GN_STATS, 0, (double)x0.n * x0.H * x0.W * C * 4.0);
-      gn_stats_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H * x0.W, sums, c.stream);
-    }
+    double* sums = stats(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x0.H * x0.W);
     ActOp a;
     a.n = nb, a.H = x0.H, a.W = x0.W, a.C = C;
     a.p = half2((size_t)nb * x0.H * x0.W * C, lo);
@@ -459,12 +464,13 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   f.gn_slot = 0;
   f.init_sums(64);
   // ---- time embedding (unet/mod.rs:19-30, 115-118) and all 22 lin_embed rows in one GEMV (:718-722)
+  float* emb_hidden = c.work.get<float>(1280);
   float* emb_silu = c.work.get<float>(1280);
   float* emb_rows = c.work.get<float>(m.emb_total);
   {
     KernelScope ks(c, KC_ELEMENTWISE);
     time_embed_launch(io.t_dev, mptr(c, m.lin1_time.wi), m.lin1_time.bias, mptr(c, m.lin2_time.wi), m.lin2_time.bias,
-                      emb_silu, c.stream);
+                      emb_hidden, emb_silu, c.stream);
   }
   {
     KernelScope ks(c, KC_ELEMENTWISE, 2.0 * 1280 * m.emb_total, 4.0 * 1280 * m.emb_total);
@@ -556,11 +562,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   }
   // out: GroupNorm + SiLU + conv 320 -> 4 (:138-140), fused, fp32 on CUDA cores, NCHW result
   {
-    double* sums = f.next_sums();
-    {
-      KernelScope ks(c, KC_GN_STATS);
-      gn_stats_launch(x.p, x.C, nullptr, 0, f.nb, H * W, sums, c.stream);
-    }
+    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 320 * 4);
     conv3x3_small_cout_launch(x.p, f.nb, H, W, 320, sums, m.norm_out.gamma, m.norm_out.beta, 1e-5f, m.conv_out.w_small,
                               m.conv_out.bias, 4, io.out, c.stream);
@@ -682,11 +684,7 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   }
   // norm_out + SiLU + conv_out 128 -> 3 (autoencoder/mod.rs:215-216)
   {
-    double* sums = f.next_sums();
-    {
-      KernelScope ks(c, KC_GN_STATS);
-      gn_stats_launch(x.p, x.C, nullptr, 0, f.nb, H * W, sums, c.stream);
-    }
+    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 128 * 3);
     conv3x3_small_cout_launch(x.p, f.nb, H, W, 128, sums, m.vae_norm_out.gamma, m.vae_norm_out.beta, 1e-5f,
                               m.vae_conv_out.w_small, m.vae_conv_out.bias, 3, d_img, c.stream);

@@ -256,8 +256,9 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   int split = 1;
   if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
     const int ctas = m_tiles * n_tiles;
-    if (ctas < 112 && iters >= 16) {
-      split = std::min(std::min((148 + ctas - 1) / ctas, iters / 8), 16);
+    if (ctas <= 74 && iters >= 16) {
+      // floor: ctas*split must stay within ONE wave of the 148 SMs (a 2-wave grid costs 2x, see profiles/r1)
+      split = std::min(std::min(148 / ctas, iters / 8), 16);
       if (split < 1) split = 1;
     }
   }
