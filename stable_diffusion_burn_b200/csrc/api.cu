@@ -61,6 +61,7 @@ int sdb_create(int device, sdb_ctx** out) {
     h = new sdb_ctx();
     h->c.device = device;
     h->c.debug_sync = getenv("SDB_DEBUG_SYNC") && atoi(getenv("SDB_DEBUG_SYNC")) != 0;
+    if (getenv("SDB_CLUSTER")) h->c.opt_cluster = atoi(getenv("SDB_CLUSTER"));
     SDB_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
     model_create(h->c);
     *out = h;
@@ -220,6 +221,8 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_graphs = value;
   else if (k == "splitk")
     c.opt_splitk = value;
+  else if (k == "cluster")
+    c.opt_cluster = value;
   else
     throw Error("unknown option: " + k);
   model_invalidate_graphs(c);

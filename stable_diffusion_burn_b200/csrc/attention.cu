@@ -14,6 +14,8 @@
 // S_g(j+1) is issued as soon as the group has copied S_g(j) to registers, so QK^T overlaps the exponentials.
 #include "attention.cuh"
 
+#include <type_traits>
+
 namespace sdb {
 
 template <int DPAD, int NG>
@@ -222,25 +224,34 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         }
       }
       float sum = 0.f;
+      const uint32_t prow_s = smem_u32(prow);
+      auto emit = [&](auto masked) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
-        __half2 hp[4];
+        for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
+          uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i0 = u * 8 + 2 * e;
-          float p0 = ex2(fmaf(__uint_as_float(sv[i0]), sl2, -m_new));
-          float p1 = ex2(fmaf(__uint_as_float(sv[i0 + 1]), sl2, -m_new));
-          if (valid != 128) {
-            p0 = (i0 < valid) ? p0 : 0.f;
-            p1 = (i0 + 1 < valid) ? p1 : 0.f;
+          for (int e = 0; e < 4; ++e) {
+            const int i0 = u * 8 + 2 * e;
+            float p0 = ex2(fmaf(__uint_as_float(sv[i0]), sl2, -m_new));
+            float p1 = ex2(fmaf(__uint_as_float(sv[i0 + 1]), sl2, -m_new));
+            if (decltype(masked)::value) {
+              p0 = (i0 < valid) ? p0 : 0.f;
+              p1 = (i0 + 1 < valid) ? p1 : 0.f;
+            }
+            sum += p0 + p1;  // fp32 terms; the fp16 rounding of P is unbiased and averages out over the row
+            const __half2 hp = __floats2half2_rn(p0, p1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&hp);
           }
-          hp[e] = __floats2half2_rn(p0, p1);
-          const float2 pf = __half22float2(hp[e]);  // the row sum uses the values the MMA will see
-          sum += pf.x + pf.y;
+          const int chunk = u >> 3, uu = u & 7;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + chunk * 16384 + ((uu ^ (r & 7)) << 4)),
+                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
         }
-        const int chunk = u >> 3, uu = u & 7;
-        *reinterpret_cast<uint4*>(prow + chunk * 16384 + ((uu ^ (r & 7)) << 4)) = *reinterpret_cast<uint4*>(hp);
-      }
+      };
+      if (valid == 128)
+        emit(std::false_type{});
+      else
+        emit(std::true_type{});
       l_run = l_run * alpha + sum;
       m_run = m_new;
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy

@@ -12,6 +12,8 @@
 // (A_lo*B_hi, A_hi*B_lo) into the same accumulator for fp32-class accuracy.
 #include "gemm_tc.cuh"
 
+#include <cstring>
+
 namespace sdb {
 
 static constexpr int BM = 128;
@@ -55,10 +57,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int it_begin = blockIdx.z * per_split;
   const int it_end = min(total_iters, it_begin + per_split);
 
+  const bool paired = p.cluster == 2;
+  const uint32_t crank = paired ? cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], paired ? 2 : 1);  // paired: both consumers must release a stage (either CTA writes into both)
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
@@ -74,7 +78,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (paired)
+    cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast into its smem
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -95,8 +102,16 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
         if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
         uint8_t* sb = st + L::A_TILES * A_TILE_BYTES;
-        tma_load_2d(sb, &maps.b[0], &full_bar[s], it * BK, col0);
-        if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &maps.b[1], &full_bar[s], it * BK, col0);
+        if (!paired) {
+          tma_load_2d(sb, &maps.b[0], &full_bar[s], it * BK, col0);
+          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &maps.b[1], &full_bar[s], it * BK, col0);
+        } else {
+          // this CTA fetches rows [crank*BN/2, +BN/2) of the weight tile for BOTH CTAs of the pair
+          constexpr int HALF = (BN / 2) * BK * 2;
+          tma_load_2d_mc(sb + crank * HALF, &maps.b[0], &full_bar[s], it * BK, col0 + crank * (BN / 2), 0x3);
+          if (PASSES >= 3)
+            tma_load_2d_mc(sb + L::B_TILE_BYTES + crank * HALF, &maps.b[1], &full_bar[s], it * BK, col0 + crank * (BN / 2), 0x3);
+        }
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
@@ -125,7 +140,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           if (PASSES >= 2) umma_f16(tmem_base, make_sdesc_sw128(a_lo + koff), db, idesc, 1u);
           if (PASSES >= 3) umma_f16(tmem_base, da, make_sdesc_sw128(b_lo + koff), idesc, 1u);
         }
-        umma_commit(&empty_bar[s]);                      // frees the smem slot when these MMAs retire
+        if (paired)
+          umma_commit_mc(&empty_bar[s], 0x3);            // release the slot in both CTAs of the pair
+        else
+          umma_commit(&empty_bar[s]);                    // frees the smem slot when these MMAs retire
         if (it == it_end - 1) umma_commit(accum_bar);    // accumulator complete
       }
       __syncwarp();
@@ -136,34 +154,53 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
   } else {
     // ===================================================== epilogue (warps 2..5)
+    // Each thread owns one accumulator row in TMEM. A row-per-thread store pattern would touch 32 different
+    // cache lines per instruction, so every 32x32 block is transposed through shared memory (the pipeline
+    // stages are idle by now) and written/read as 4 rows x 128 contiguous bytes per warp instruction.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;        // accumulator row
     const int pw = w0 + r % p.TW;
     const int phh = h0 + (r / p.TW) % p.TH;
     const int pn = n0 + r / (p.TW * p.TH);
-    const bool row_ok = (pw < p.W) && (phh < p.H) && (pn < p.nimg);
+    const int row_ok = ((pw < p.W) && (phh < p.H) && (pn < p.nimg)) ? 1 : 0;
     const long long m = ((long long)pn * p.OH + (long long)phh * p.os + p.oa) * p.OW + (long long)pw * p.os + p.ob;
 
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (2 * 32 * 33);  // two 32x33 fp32 tiles per warp
+    float* tile2 = tile + 32 * 33;
+    const int sub = lane >> 3;          // row within a group of 4
+    const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
+
+    auto stage = [&](float* t, const uint32_t (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[lane * 33 + j] = __uint_as_float(v[j]);
+    };
 
     if (p.split_k > 1) {
       // raw partial sums -> workspace [split][M][N]
       const long long Mtot = (long long)p.nimg * p.OH * p.OW;
-      float* wsrow = p.ws + ((long long)blockIdx.z * Mtot + m) * p.N + col0;
+      float* wsbase = p.ws + (long long)blockIdx.z * Mtot * p.N;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        if (row_ok && col0 + c < p.N) {
+        stage(tile, v);
+        __syncwarp();
+        const int col = col0 + c + cq;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(wsrow + c + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub;
+          const long long mr = __shfl_sync(0xffffffffu, m, rr);
+          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
+          if (okr && col < p.N) {
+            const float* t = tile + rr * 33 + cq;
+            *reinterpret_cast<float4*>(wsbase + mr * p.N + col) = make_float4(t[0], t[1], t[2], t[3]);
+          }
         }
+        __syncwarp();
       }
     } else if (p.geglu) {
       // tile columns [0,BN/2) = x, [BN/2,BN) = gate; output columns blockIdx.y*BN/2 + [0,BN/2)
@@ -171,28 +208,39 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const int ocol0 = blockIdx.y * HB;
 #pragma unroll 1
       for (int c = 0; c < HB; c += 32) {
-        uint32_t vx[32], vg[32];
-        tmem_ld32(trow + c, vx);
-        tmem_ld32(trow + HB + c, vg);
+        uint32_t v[32];
+        tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        if (row_ok && col0 + c < p.N) {
-          __half* o = p.out_f16 + m * p.ldc16 + ocol0 + c;
-          __half* ol = p.out_f16_lo ? p.out_f16_lo + m * p.ldc16 + ocol0 + c : nullptr;
+        stage(tile, v);
+        tmem_ld32(trow + HB + c, v);
+        tmem_ld_wait();
+        stage(tile2, v);
+        __syncwarp();
+        const float4 bx = *reinterpret_cast<const float4*>(p.bias + col0 + c + cq);
+        const float4 bg = *reinterpret_cast<const float4*>(p.bias + col0 + HB + c + cq);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0 = __uint_as_float(vx[j]) + p.bias[col0 + c + j];
-            float x1 = __uint_as_float(vx[j + 1]) + p.bias[col0 + c + j + 1];
-            float g0 = __uint_as_float(vg[j]) + p.bias[col0 + HB + c + j];
-            float g1 = __uint_as_float(vg[j + 1]) + p.bias[col0 + HB + c + j + 1];
-            float y0 = x0 * gelu_erf_fast(g0), y1 = x1 * gelu_erf_fast(g1);
-            __half2 h = __floats2half2_rn(y0, y1);
-            *reinterpret_cast<__half2*>(o + j) = h;
-            if (ol) {
-              float2 hf = __half22float2(h);
-              *reinterpret_cast<__half2*>(ol + j) = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub;
+          const long long mr = __shfl_sync(0xffffffffu, m, rr);
+          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
+          if (okr && col0 + c < p.N) {
+            const float* tx = tile + rr * 33 + cq;
+            const float* tg = tile2 + rr * 33 + cq;
+            const float y0 = (tx[0] + bx.x) * gelu_erf_fast(tg[0] + bg.x);
+            const float y1 = (tx[1] + bx.y) * gelu_erf_fast(tg[1] + bg.y);
+            const float y2 = (tx[2] + bx.z) * gelu_erf_fast(tg[2] + bg.z);
+            const float y3 = (tx[3] + bx.w) * gelu_erf_fast(tg[3] + bg.w);
+            __half2 h[2] = {__floats2half2_rn(y0, y1), __floats2half2_rn(y2, y3)};
+            const long long o = mr * p.ldc16 + ocol0 + c + cq;
+            *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
+            if (p.out_f16_lo) {
+              const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+              __half2 l[2] = {__floats2half2_rn(y0 - f0.x, y1 - f0.y), __floats2half2_rn(y2 - f1.x, y3 - f1.y)};
+              *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
             }
           }
         }
+        __syncwarp();
       }
     } else {
 #pragma unroll 1
@@ -200,60 +248,52 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        if (row_ok && col0 + c < p.N) {
-          const int col = col0 + c;
-          float f[32];
+        stage(tile, v);
+        __syncwarp();
+        const int col = col0 + c + cq;
+        const bool col_ok = col < p.N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
-              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub;
+          const long long mr = __shfl_sync(0xffffffffu, m, rr);
+          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
+          const int pnr = __shfl_sync(0xffffffffu, pn, rr);
+          if (okr && col_ok) {
+            const float* t = tile + rr * 33 + cq;
+            float4 f = make_float4(t[0] + bv.x, t[1] + bv.y, t[2] + bv.z, t[3] + bv.w);
+            if (p.rowbias) {
+              const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (long long)pnr * p.N + col);
+              f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
             }
-          }
-          if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)pn * p.N + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = *reinterpret_cast<const float4*>(rb + j);
-              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+            if (p.residual) {
+              const float4 b = *reinterpret_cast<const float4*>(p.residual + mr * p.ldc + col);
+              f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
             }
-          }
-          if (p.residual) {
-            const float* rs = p.residual + m * p.ldc + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = *reinterpret_cast<const float4*>(rs + j);
-              f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
-            }
-          }
-          if (p.out_f32) {
-            float* o = p.out_f32 + m * p.ldc + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-          if (p.out_f16) {
-            __half* o = p.out_f16 + m * p.ldc16 + col;
-            __half* ol = p.out_f16_lo ? p.out_f16_lo + m * p.ldc16 + col : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              __half2 h = __floats2half2_rn(f[j], f[j + 1]);
-              *reinterpret_cast<__half2*>(o + j) = h;
-              if (ol) {
-                float2 hf = __half22float2(h);
-                *reinterpret_cast<__half2*>(ol + j) = __floats2half2_rn(f[j] - hf.x, f[j + 1] - hf.y);
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + mr * p.ldc + col) = f;
+            if (p.out_f16) {
+              __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
+              const long long o = mr * p.ldc16 + col;
+              *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
+              if (p.out_f16_lo) {
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                __half2 l[2] = {__floats2half2_rn(f.x - f0.x, f.y - f0.y), __floats2half2_rn(f.z - f1.x, f.w - f1.y)};
+                *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
               }
             }
           }
         }
+        __syncwarp();
       }
     }
     tc_fence_before();
   }
 
-  __syncthreads();
+  if (paired)
+    cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -333,15 +373,21 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
     attr_set = true;
   }
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
-  gemm_tc_kernel<BN, PASSES, STAGES><<<grid, 192, smem, stream>>>(maps, p);
-  SDB_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = dim3(192), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES>, maps, p));
 }
 
 template <int BN, int PASSES>
 static void launch_bn(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * p.split_k;
   // many short tiles: two co-resident CTAs per SM overlap one tile's epilogue with the other's mainloop
-  if (ctas >= 2 * 148 && pick_stages_half<BN, PASSES>() * StageLayout<BN, PASSES>::BYTES <= 104 * 1024)
+  if (p.cluster == 1 && ctas >= 2 * 148 && pick_stages_half<BN, PASSES>() * StageLayout<BN, PASSES>::BYTES <= 104 * 1024)
     launch_inst<BN, PASSES, pick_stages_half<BN, PASSES>()>(maps, p, stream);
   else
     launch_inst<BN, PASSES, pick_stages<BN, PASSES>()>(maps, p, stream);
@@ -350,6 +396,7 @@ static void launch_bn(const GemmMaps& maps, const GemmParams& p, cudaStream_t st
 void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream) {
   SDB_CHECK(p.TN * p.TH * p.TW == BM, "M tile must cover 128 rows");
   SDB_CHECK(p.N % 32 == 0, "N must be a multiple of 32");
+  SDB_CHECK(p.cluster == 1 || (p.cluster == 2 && (p.tiles_n * p.tiles_h * p.tiles_w) % 2 == 0), "cluster pairing needs an even M-tile count");
 #define SDB_DISPATCH(bn)                                             \
   case bn:                                                           \
     if (passes == 1) launch_bn<bn, 1>(maps, p, stream);              \

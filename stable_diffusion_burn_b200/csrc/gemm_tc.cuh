@@ -10,7 +10,8 @@ namespace sdb {
 // D (fp32, TMEM) [128 rows = TN*TH*TW output pixels][BN output channels].
 struct GemmMaps {
   CUtensorMap a[2][2];  // [source 0/1][hi/lo]
-  CUtensorMap b[2];     // [hi/lo]
+  CUtensorMap b[2];     // [hi/lo]  box {64, BN}   (cluster = 1)  or  {64, BN/2} (cluster = 2: each CTA of an
+                        //          M-pair fetches half of the shared weight tile and multicasts it to both)
 };
 
 struct GemmParams {
@@ -23,6 +24,7 @@ struct GemmParams {
   int num_taps;
   int8_t tap_dh[9], tap_dw[9], tap_ph[9];
   int split_k;
+  int cluster;             // 1, or 2 = CTA pairs along M share every weight tile through TMA multicast
   // epilogue
   float* out_f32;          // [M][ldc] or null
   __half* out_f16;         // [M][ldc16] or null (hi part)

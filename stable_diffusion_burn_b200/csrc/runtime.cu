@@ -239,17 +239,25 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.tiles_n = (a0.n + p.TN - 1) / p.TN;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 
-  // N tile
+  // CTA pairs along M share each weight tile (TMA multicast): halves the weight-tile L2->smem traffic, which is
+  // what bounds these kernels (profiles/r1_gemm_tc_ncu_full.md). Needs an even number of M tiles.
+  const bool pair = c.opt_cluster && (m_tiles % 2 == 0);
+  // N tile: as wide as N allows — operand bytes per FLOP fall with the tile area
   int BN;
   if (ep.geglu)
     BN = 128;
-  else if (w.N % 128 == 0)
-    BN = (w.N % 256 == 0 && (long long)m_tiles * (w.N / 256) >= 296) ? 256 : 128;
+  else if (w.N % 256 == 0 && (pair || (long long)m_tiles * (w.N / 256) >= 296) && (long long)m_tiles * (w.N / 256) >= 64)
+    BN = 256;
+  else if (w.N % 128 == 0 && w.N % 160 != 0)
+    BN = 128;
   else if (w.N % 160 == 0)
     BN = 160;
+  else if (w.N % 128 == 0)
+    BN = 128;
   else
     BN = 64;
   const int n_tiles = (w.N + BN - 1) / BN;
+  p.cluster = pair ? 2 : 1;
 
   // split-K when the grid cannot fill the machine and the K loop is long
   const int iters = p.num_taps * p.kc;
@@ -269,8 +277,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.split_k = split;
   if (c.debug_sync) {
     char buf[256];
-    snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d",
-             kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW);
+    snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d cluster=%d",
+             kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW, p.cluster);
     c.dbg_label = buf;
   }
 
@@ -309,9 +317,10 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
     const __half* wlo = w.p.lo ? w.p.lo + (size_t)phase * w.N * w.K : nullptr;
     const int wrows = w.rows ? w.rows : w.N;
-    maps.b[0] = make_w_map(whi, w.K, wrows, BN, w.ld);
+    const int bbox = pair ? BN / 2 : BN;
+    maps.b[0] = make_w_map(whi, w.K, wrows, bbox, w.ld);
     maps.b[1] = maps.b[0];
-    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, wrows, BN, w.ld);
+    if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, wrows, bbox, w.ld);
     if (kind == G_CONV3_UP2) {
       const int a = phase >> 1, b = phase & 1;
       p.oa = a, p.ob = b;

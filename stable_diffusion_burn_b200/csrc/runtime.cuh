@@ -90,6 +90,7 @@ struct Ctx {
   int opt_precision = 0;  // 0 = per-layer policy, 1/2/3 = force
   int opt_graphs = 1;
   int opt_splitk = 1;
+  int opt_cluster = 1;    // CTA-pair TMA multicast of weight tiles
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> prof;
