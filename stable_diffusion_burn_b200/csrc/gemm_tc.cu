@@ -29,7 +29,7 @@ struct StageLayout {
 };
 
 template <int BN, int PASSES, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 2)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using L = StageLayout<BN, PASSES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -39,6 +39,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint32_t* tile_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,11 +154,13 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    // Each thread owns one accumulator row in TMEM. A row-per-thread store pattern would touch 32 different
-    // cache lines per instruction, so every 32x32 block is transposed through shared memory (the pipeline
-    // stages are idle by now) and written/read as 4 rows x 128 contiguous bytes per warp instruction.
+    // ===================================================== epilogue (warps 2..9)
+    // Each thread owns one accumulator row in TMEM (warp w may touch lanes 32*(w%4)..+31); the two warps that
+    // share a lane quarter split the 32-column chunks between them. A row-per-thread store pattern would touch 32
+    // cache lines per instruction, so every 32x32 block is transposed through shared memory (the pipeline stages
+    // are idle by now) and written/read as 4 rows x 128 contiguous bytes per warp instruction.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the column chunks this warp owns
     const int r = q * 32 + lane;        // accumulator row
     const int pw = w0 + r % p.TW;
     const int phh = h0 + (r / p.TW) % p.TH;
@@ -177,13 +180,37 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[lane * 33 + j] = __uint_as_float(v[j]);
     };
+    // bias / time-embedding row / residual / fp32 + fp16(hi,lo) stores for 4 consecutive columns of one output row
+    auto finish = [&](float4 f, long long mr, int pnr, int col, const float4& bv) {
+      f.x += bv.x, f.y += bv.y, f.z += bv.z, f.w += bv.w;
+      if (p.rowbias) {
+        const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (long long)pnr * p.N + col);
+        f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
+      }
+      if (p.residual) {
+        const float4 b = *reinterpret_cast<const float4*>(p.residual + mr * p.ldc + col);
+        f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
+      }
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + mr * p.ldc + col) = f;
+      if (p.out_f16) {
+        __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
+        const long long o = mr * p.ldc16 + col;
+        *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
+        if (p.out_f16_lo) {
+          const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+          __half2 l[2] = {__floats2half2_rn(f.x - f0.x, f.y - f0.y), __floats2half2_rn(f.z - f1.x, f.w - f1.y)};
+          *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
+        }
+      }
+    };
 
     if (p.split_k > 1) {
-      // raw partial sums -> workspace [split][M][N]
+      // raw partial sums -> workspace [split][M][N]; the LAST CTA of this tile (ticket) folds the splits in z order
+      // (deterministic) and runs the epilogue — no separate reduction launch.
       const long long Mtot = (long long)p.nimg * p.OH * p.OW;
       float* wsbase = p.ws + (long long)blockIdx.z * Mtot * p.N;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
@@ -197,17 +224,53 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
           if (okr && col < p.N) {
             const float* t = tile + rr * 33 + cq;
-            *reinterpret_cast<float4*>(wsbase + mr * p.N + col) = make_float4(t[0], t[1], t[2], t[3]);
+            __stcg(reinterpret_cast<float4*>(wsbase + mr * p.N + col), make_float4(t[0], t[1], t[2], t[3]));
           }
         }
         __syncwarp();
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have published their part of the tile
+      uint32_t* flag = reinterpret_cast<uint32_t*>(tile_flag);
+      if (warp == 2 && lane == 0) {
+        unsigned int* tk = p.tickets + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned int old = atomicAdd(tk, 1u);
+        const bool last = old == (unsigned)(p.split_k - 1);
+        if (last) *tk = 0u;  // self-cleaning: the buffer is all zero again for the next launch
+        *flag = last ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (*flag) {
+        __threadfence();
+#pragma unroll 1
+        for (int c = half * 32; c < BN; c += 64) {
+          const int col = col0 + c + cq;
+          const bool col_ok = col < p.N;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + sub;
+            const long long mr = __shfl_sync(0xffffffffu, m, rr);
+            const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
+            const int pnr = __shfl_sync(0xffffffffu, pn, rr);
+            if (okr && col_ok) {
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int z = 0; z < p.split_k; ++z) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + mr) * p.N + col));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              finish(acc, mr, pnr, col, bv);
+            }
+          }
+        }
       }
     } else if (p.geglu) {
       // tile columns [0,BN/2) = x, [BN/2,BN) = gate; output columns blockIdx.y*BN/2 + [0,BN/2)
       constexpr int HB = BN / 2;
       const int ocol0 = blockIdx.y * HB;
 #pragma unroll 1
-      for (int c = 0; c < HB; c += 32) {
+      for (int c = half * 32; c < HB; c += 64) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
@@ -244,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     } else {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
@@ -262,26 +325,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const int pnr = __shfl_sync(0xffffffffu, pn, rr);
           if (okr && col_ok) {
             const float* t = tile + rr * 33 + cq;
-            float4 f = make_float4(t[0] + bv.x, t[1] + bv.y, t[2] + bv.z, t[3] + bv.w);
-            if (p.rowbias) {
-              const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (long long)pnr * p.N + col);
-              f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
-            }
-            if (p.residual) {
-              const float4 b = *reinterpret_cast<const float4*>(p.residual + mr * p.ldc + col);
-              f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
-            }
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + mr * p.ldc + col) = f;
-            if (p.out_f16) {
-              __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
-              const long long o = mr * p.ldc16 + col;
-              *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
-              if (p.out_f16_lo) {
-                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                __half2 l[2] = {__floats2half2_rn(f.x - f0.x, f.y - f0.y), __floats2half2_rn(f.z - f1.x, f.w - f1.y)};
-                *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
-              }
-            }
+            finish(make_float4(t[0], t[1], t[2], t[3]), mr, pnr, col, bv);
           }
         }
         __syncwarp();
@@ -375,7 +419,7 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid, cfg.blockDim = dim3(192), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cfg.gridDim = grid, cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;

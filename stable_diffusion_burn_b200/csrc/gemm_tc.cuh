@@ -36,6 +36,7 @@ struct GemmParams {
   int ldc16;               // row stride of out_f16
   int geglu;               // 1: columns are (x|gate) interleaved per tile, output width N/2
   float* ws;               // split-K workspace [split][M][N]
+  unsigned int* tickets;   // split-K: one counter per output tile, all zero between launches (self-cleaning)
   // output pixel mapping: out row = ((n*OH + h*os + oa)*OW + w*os + ob)
   int OH, OW, os, oa, ob;
 };

@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   const int C = C0 + C1, gs = C / 32;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
+  // thread -> (channel pair, pixel lane): narrow tensors (C/2 < 256) spread the spare threads over pixels
+  const int npair = C / 2;
+  const int pg = npair >= 256 ? 1 : 256 / npair;          // pixel lanes per channel pair
+  const int nslot = npair >= 256 ? npair : npair * pg;    // (pixel lane, pair) partials, <= 1280
+  for (int slot = threadIdx.x; slot < nslot; slot += blockDim.x) {
+    const int cp = slot % npair, pl = slot / npair;
     const int c = cp * 2;
     const float* ptr;
     int stride;
@@ -49,23 +54,23 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
       stride = C1;
     }
     float s = 0.f, q = 0.f;
-    int p = p0;
-    for (; p + 4 <= p1; p += 4) {
+    int p = p0 + pl;
+    for (; p + 3 * pg < p1; p += 4 * pg) {
       float2 v0 = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
-      float2 v1 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 1) * stride);
-      float2 v2 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 2) * stride);
-      float2 v3 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 3) * stride);
+      float2 v1 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + pg) * stride);
+      float2 v2 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 2 * pg) * stride);
+      float2 v3 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 3 * pg) * stride);
       s += (v0.x + v0.y) + (v1.x + v1.y) + (v2.x + v2.y) + (v3.x + v3.y);
       q += (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) + (v2.x * v2.x + v2.y * v2.y) +
            (v3.x * v3.x + v3.y * v3.y);
     }
-    for (; p < p1; ++p) {
+    for (; p < p1; p += pg) {
       float2 v = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
       s += v.x + v.y;
       q += v.x * v.x + v.y * v.y;
     }
-    s_pair[0][cp] = s;
-    s_pair[1][cp] = q;
+    s_pair[0][slot] = s;
+    s_pair[1][slot] = q;
   }
   __syncthreads();
   const int chunks = gridDim.x;
@@ -73,7 +78,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
     const int pairs = gs / 2;
     float acc = 0.f;
-    for (int i = 0; i < pairs; ++i) acc += s_pair[which][g * pairs + i];
+    for (int l = 0; l < (npair >= 256 ? 1 : pg); ++l)
+      for (int i = 0; i < pairs; ++i) acc += s_pair[which][l * npair + g * pairs + i];
     partials[((size_t)n * chunks + blockIdx.x) * 64 + threadIdx.x] = acc;
   }
   __threadfence();
@@ -182,6 +188,147 @@ void prep_operand_launch(const float* x0, int C0, const float* x1, int C1, int n
   dim3 grid(ceil_div(HW, pix), n);
   const size_t smem = (mode & PREP_NORM) ? (size_t)2 * C * sizeof(float) : 0;
   prep_operand_kernel<<<grid, 256, smem, st>>>(x0, C0, x1, C1, H, W, pix, mode, sums, gamma, beta, eps, out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// ============================================================ fused GroupNorm: statistics + apply in ONE launch
+// Phase 1: per-CTA group partials of the CTA's pixel chunk (fixed-order, deterministic); the last CTA of an image
+// folds them and raises a flag. Phase 2 (after an in-kernel wait on that flag): normalise + SiLU + fp16 hi/lo split
+// of the same chunk (second read hits L2). The grid never exceeds 4 CTAs per SM, so every CTA is resident and the
+// wait cannot deadlock.
+__global__ void __launch_bounds__(256)
+gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int H, int W, int pix_per_cta,
+                int silu, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                __half* __restrict__ out_hi, __half* __restrict__ out_lo, double* __restrict__ sums,
+                float* __restrict__ partials, unsigned int* __restrict__ tickets, unsigned int* __restrict__ flags) {
+  extern __shared__ float s_dyn[];  // scale[C], shift[C]
+  __shared__ float s_pair[2][1280];
+  __shared__ bool s_last;
+  const int n = blockIdx.y;
+  const int C = C0 + C1, gs = C / 32, HW = H * W;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  // ---- phase 1
+  // thread -> (channel pair, pixel lane): narrow tensors (C/2 < 256) spread the spare threads over pixels
+  const int npair = C / 2;
+  const int pg = npair >= 256 ? 1 : 256 / npair;          // pixel lanes per channel pair
+  const int nslot = npair >= 256 ? npair : npair * pg;    // (pixel lane, pair) partials, <= 1280
+  for (int slot = threadIdx.x; slot < nslot; slot += blockDim.x) {
+    const int cp = slot % npair, pl = slot / npair;
+    const int c = cp * 2;
+    const float* ptr;
+    int stride;
+    if (c < C0) {
+      ptr = x0 + (size_t)n * HW * C0 + c;
+      stride = C0;
+    } else {
+      ptr = x1 + (size_t)n * HW * C1 + (c - C0);
+      stride = C1;
+    }
+    float s = 0.f, q = 0.f;
+    int p = p0 + pl;
+    for (; p + 3 * pg < p1; p += 4 * pg) {
+      float2 v0 = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
+      float2 v1 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + pg) * stride);
+      float2 v2 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 2 * pg) * stride);
+      float2 v3 = *reinterpret_cast<const float2*>(ptr + (size_t)(p + 3 * pg) * stride);
+      s += (v0.x + v0.y) + (v1.x + v1.y) + (v2.x + v2.y) + (v3.x + v3.y);
+      q += (v0.x * v0.x + v0.y * v0.y) + (v1.x * v1.x + v1.y * v1.y) + (v2.x * v2.x + v2.y * v2.y) +
+           (v3.x * v3.x + v3.y * v3.y);
+    }
+    for (; p < p1; p += pg) {
+      float2 v = *reinterpret_cast<const float2*>(ptr + (size_t)p * stride);
+      s += v.x + v.y;
+      q += v.x * v.x + v.y * v.y;
+    }
+    s_pair[0][slot] = s;
+    s_pair[1][slot] = q;
+  }
+  __syncthreads();
+  const int chunks = gridDim.x;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int pairs = gs / 2;
+    float acc = 0.f;
+    for (int l = 0; l < (npair >= 256 ? 1 : pg); ++l)
+      for (int i = 0; i < pairs; ++i) acc += s_pair[which][l * npair + g * pairs + i];
+    partials[((size_t)n * chunks + blockIdx.x) * 64 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1u) == (unsigned)(chunks - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < 64) {
+      __threadfence();
+      double acc = 0.0;
+      for (int ch = 0; ch < chunks; ++ch) acc += (double)__ldcg(&partials[((size_t)n * chunks + ch) * 64 + threadIdx.x]);
+      sums[(size_t)n * 64 + threadIdx.x] = acc;  // [n][32][2]
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(&flags[n], 1u);
+  }
+  // ---- wait for the image's statistics
+  if (threadIdx.x == 0) {
+    while (atomicAdd(&flags[n], 0u) == 0u) __nanosleep(100);
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2
+  float* s_scale = s_dyn;
+  float* s_shift = s_dyn + C;
+  {
+    const double inv_cnt = 1.0 / ((double)gs * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / gs;
+      const double sm = __ldcg(&sums[((size_t)n * 32 + g) * 2 + 0]), sq = __ldcg(&sums[((size_t)n * 32 + g) * 2 + 1]);
+      const double mean = sm * inv_cnt;
+      double var = sq * inv_cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float sc = rstd * gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = beta[c] - (float)mean * sc;
+    }
+  }
+  __syncthreads();
+  const int c8n = C / 8;
+  const int items = (p1 - p0) * c8n;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int p = p0 + i / c8n;
+    const int c = (i % c8n) * 8;
+    const float* src = (c < C0) ? x0 + ((size_t)n * HW + p) * C0 + c : x1 + ((size_t)n * HW + p) * C1 + (c - C0);
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b = *reinterpret_cast<const float4*>(src + 4);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * s_scale[c + j] + s_shift[c + j];
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+    const size_t o = ((size_t)n * HW + p) * C + c;
+    split_store8(f, out_hi + o, out_lo ? out_lo + o : nullptr);
+  }
+}
+
+static int gn_fused_pix(int n, int HW) {
+  int pix = (int)((((long long)HW * n) + 591) / 592);
+  return pix < 8 ? 8 : pix;
+}
+size_t gn_fused_partial_floats(int n, int HW) { return (size_t)n * ceil_div(HW, gn_fused_pix(n, HW)) * 64; }
+
+void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int silu, const float* gamma,
+                     const float* beta, float eps, Half2Ptr out, double* sums, float* partials, unsigned int* tickets,
+                     unsigned int* flags, cudaStream_t st) {
+  const int C = C0 + C1, HW = H * W;
+  SDB_CHECK(C % 64 == 0 && C0 % 8 == 0 && C <= 2560, "GroupNorm channels");
+  const int pix = gn_fused_pix(n, HW);
+  dim3 grid(ceil_div(HW, pix), n);
+  SDB_CHECK((long long)grid.x * grid.y <= 592, "fused GroupNorm grid must stay co-resident");
+  gn_fused_kernel<<<grid, 256, (size_t)2 * C * sizeof(float), st>>>(x0, C0, x1, C1, H, W, pix, silu, gamma, beta, eps, out.hi,
+                                                                     out.lo, sums, partials, tickets, flags);
   SDB_CUDA(cudaGetLastError());
 }
 

@@ -17,6 +17,12 @@ struct Half2Ptr {
 size_t gn_stats_partial_floats(int n, int HW);
 void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, float* partials,
                      unsigned int* tickets, cudaStream_t st);
+// One-launch GroupNorm(+SiLU) -> fp16 hi(/lo) operand: statistics and apply fused through an in-kernel grid wait.
+// tickets/flags: [n] zeroed counters; partials: gn_fused_partial_floats(n,HW) floats of scratch.
+size_t gn_fused_partial_floats(int n, int HW);
+void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int silu, const float* gamma,
+                     const float* beta, float eps, Half2Ptr out, double* sums, float* partials, unsigned int* tickets,
+                     unsigned int* flags, cudaStream_t st);
 // mode bits
 enum : int { PREP_NORM = 1, PREP_SILU = 2, PREP_UP2 = 4, PREP_PHASE2 = 8 };
 // Stages a conv/GEMM A operand: y = [silu]([groupnorm](cat(x0,x1))) -> fp16 hi(/lo).

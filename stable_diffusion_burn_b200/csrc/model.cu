@@ -203,14 +203,14 @@ struct Fwd {
   void init_sums(int slots) {
     gn_slots = slots;
     gn_sums = c.work.get<double>((size_t)slots * nb * 64);
-    gn_tickets = c.work.get<unsigned int>((size_t)slots * nb);
-    SDB_CUDA(cudaMemsetAsync(gn_tickets, 0, sizeof(unsigned int) * slots * nb, c.stream));
+    gn_tickets = c.work.get<unsigned int>((size_t)slots * nb * 2);  // tickets | flags
+    SDB_CUDA(cudaMemsetAsync(gn_tickets, 0, sizeof(unsigned int) * slots * nb * 2, c.stream));
   }
   // GroupNorm statistics of cat(x0,x1): returns the [nb][32][2] sums
   double* stats(const float* x0, int C0, const float* x1, int C1, int HW) {
     SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
     double* sums = gn_sums + (size_t)gn_slot * nb * 64;
-    unsigned int* tk = gn_tickets + (size_t)gn_slot * nb;
+    unsigned int* tk = gn_tickets + (size_t)gn_slot * nb * 2;
     gn_slot++;
     float* part = c.work.get<float>(gn_stats_partial_floats(nb, HW));
     KernelScope ks(c, KC_GN_STATS, 0, (double)nb * HW * (C0 + C1) * 4.0);
@@ -232,15 +232,18 @@ struct Fwd {
   // GroupNorm(+SiLU) of cat(x0,x1) staged as an fp16 operand
   ActOp gn_operand(const Act& x0, const Act* x1, const NormW& nw, bool silu, bool lo) {
     const int C = x0.C + (x1 ? x1->C : 0);
-    double* sums = stats(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x0.H * x0.W);
     ActOp a;
     a.n = nb, a.H = x0.H, a.W = x0.W, a.C = C;
     a.p = half2((size_t)nb * x0.H * x0.W * C, lo);
-    {
-      KernelScope ks(c, KC_PREP, 0, (double)x0.n * x0.H * x0.W * C * (4.0 + 2.0 + (lo ? 2.0 : 0.0)));
-      prep_operand_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W,
-                          PREP_NORM | (silu ? PREP_SILU : 0), sums, nw.gamma, nw.beta, 1e-5f, a.p, c.stream);
-    }
+    SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
+    double* sums = gn_sums + (size_t)gn_slot * nb * 64;
+    unsigned int* tk = gn_tickets + (size_t)gn_slot * nb * 2;
+    gn_slot++;
+    const int HW = x0.H * x0.W;
+    float* part = c.work.get<float>(gn_fused_partial_floats(nb, HW));
+    KernelScope ks(c, KC_PREP, 0, (double)nb * HW * C * (8.0 + 2.0 + (lo ? 2.0 : 0.0)));
+    gn_fused_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, 1e-5f,
+                    a.p, sums, part, tk, tk + nb, c.stream);
     return a;
   }
   // raw (un-normalised) fp16 staging; mode 0, PREP_PHASE2 (stride-2 conv input)

@@ -198,6 +198,8 @@ void model_create(Ctx& c) {
   c.master.off = b.off * sizeof(float);
   c.packed.init(env_gb("SDB_PACKED_GB", 5.5));
   c.work.init(env_gb("SDB_WORK_GB", 24.0));
+  SDB_CUDA(cudaMalloc(&c.splitk_tickets, 65536 * sizeof(unsigned int)));
+  SDB_CUDA(cudaMemsetAsync(c.splitk_tickets, 0, 65536 * sizeof(unsigned int), c.stream));
   SDB_CUDA(cudaMemsetAsync(c.master.base, 0, c.master.cap, c.stream));
   SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
@@ -206,6 +208,7 @@ void model_destroy(Ctx& c) {
   auto* m = reinterpret_cast<Model*>(c.model);
   if (!m) return;
   model_invalidate_graphs(c);
+  if (c.splitk_tickets) cudaFree(c.splitk_tickets), c.splitk_tickets = nullptr;
   delete m;
   c.model = nullptr;
 }

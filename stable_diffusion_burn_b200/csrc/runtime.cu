@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sdb {
@@ -55,6 +56,7 @@ KernelScope::KernelScope(Ctx& c_, int cls_, double flops, double bytes) : c(c_),
     ev.cls = cls;
     ev.flops = flops;
     ev.bytes = bytes;
+    ev.label = c.dbg_label;
     cudaEventCreate(&ev.a);
     cudaEventCreate(&ev.b);
     cudaEventRecord(ev.a, c.stream);
@@ -72,19 +74,22 @@ KernelScope::~KernelScope() {
               cudaGetErrorString(e), c.dbg_label.c_str());
       fflush(stderr);
     }
-    c.dbg_label.clear();
   }
+  c.dbg_label.clear();
 }
 void profile_collect(Ctx& c) {
   if (c.prof.empty()) return;
   cudaStreamSynchronize(c.stream);
+  FILE* dump = getenv("SDB_PROFILE_DUMP") ? fopen(getenv("SDB_PROFILE_DUMP"), "a") : nullptr;
   for (auto& e : c.prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e.a, e.b);
     c.cls_ms[e.cls] += ms;
+    if (dump) fprintf(dump, "%s\t%.3f\t%.4g\t%.4g\t%s\n", kernel_class_name(e.cls), ms * 1e3, e.flops, e.bytes, e.label.c_str());
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
+  if (dump) fclose(dump);
   c.prof.clear();
 }
 
@@ -157,7 +162,7 @@ void run_attention(Ctx& c, const AttnOp& a) {
   const CUtensorMap mk = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
   const CUtensorMap mv = make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
   const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
-  if (c.debug_sync) {
+  if (c.debug_sync || c.profiling) {
     char buf[200];
     snprintf(buf, sizeof(buf), "attention nb=%d heads=%d d=%d dpad=%d Nq=%d Nk=%d ldq=%d ldk=%d ldv=%d kvlen=%p", a.nb, a.heads,
              a.d, a.dpad, a.Nq, a.Nk, a.ldq, a.ldk, a.ldv, (const void*)a.kvlen);
@@ -239,19 +244,18 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.tiles_n = (a0.n + p.TN - 1) / p.TN;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 
-  // CTA pairs along M share each weight tile (TMA multicast): halves the weight-tile L2->smem traffic, which is
-  // what bounds these kernels (profiles/r1_gemm_tc_ncu_full.md). Needs an even number of M tiles.
+  // Optional CTA pairs along M sharing each weight tile by TMA multicast ("cluster" option, default off: measured
+  // neutral on B200 — operand delivery is bounded per SM, not by L2 reads — and it forbids 2 CTAs/SM; see
+  // profiles/r1_gemm_layers.md). Needs an even number of M tiles.
   const bool pair = c.opt_cluster && (m_tiles % 2 == 0);
-  // N tile: as wide as N allows — operand bytes per FLOP fall with the tile area
+  // N tile (measured per layer in profiles/r1_gemm_layers.md): 160 divides the UNet widths 320/640/1280 evenly
   int BN;
   if (ep.geglu)
     BN = 128;
-  else if (w.N % 256 == 0 && (pair || (long long)m_tiles * (w.N / 256) >= 296) && (long long)m_tiles * (w.N / 256) >= 64)
-    BN = 256;
-  else if (w.N % 128 == 0 && w.N % 160 != 0)
-    BN = 128;
   else if (w.N % 160 == 0)
     BN = 160;
+  else if (w.N % 256 == 0 && (long long)m_tiles * (w.N / 256) >= 296)
+    BN = 256;
   else if (w.N % 128 == 0)
     BN = 128;
   else
@@ -275,7 +279,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     split = (iters + per - 1) / per;
   }
   p.split_k = split;
-  if (c.debug_sync) {
+  if (c.debug_sync || c.profiling) {
     char buf[256];
     snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d cluster=%d",
              kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW, p.cluster);
@@ -334,6 +338,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     if (split > 1) {
       const size_t need = (size_t)split * (size_t)Mtot * w.N * sizeof(float);
       p.ws = reinterpret_cast<float*>(c.work.alloc(need));
+      SDB_CHECK((long long)m_tiles * n_tiles <= 65536, "split-K ticket buffer");
+      p.tickets = c.splitk_tickets;
     }
     {
       // flops = algorithmic 2*M*N*K of this launch; the class' second counter holds the ISSUED tensor-core
@@ -342,10 +348,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       KernelScope ks(c, KC_GEMM, flops, flops * passes);
       gemm_tc_launch(maps, p, BN, passes, c.stream);
     }
-    if (split > 1) {
-      KernelScope ks(c, KC_SPLITK, 0, (double)split * Mtot * w.N * 4.0);
-      splitk_reduce_launch(p, c.stream);
-    }
+    // (the split-K reduction happens inside the kernel: the last CTA of a tile folds the partials)
   }
 }
 

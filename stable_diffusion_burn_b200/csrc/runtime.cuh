@@ -50,6 +50,7 @@ struct ProfEvent {
   int cls;
   cudaEvent_t a, b;
   double flops, bytes;
+  std::string label;
 };
 
 // fp16 activation operand [n][P][H][W][C]
@@ -90,7 +91,7 @@ struct Ctx {
   int opt_precision = 0;  // 0 = per-layer policy, 1/2/3 = force
   int opt_graphs = 1;
   int opt_splitk = 1;
-  int opt_cluster = 1;    // CTA-pair TMA multicast of weight tiles
+  int opt_cluster = 0;    // CTA-pair TMA multicast of weight tiles (measured neutral; kept as an option)
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> prof;
@@ -98,6 +99,7 @@ struct Ctx {
   double cls_ms[KC_COUNT] = {0}, cls_flops[KC_COUNT] = {0}, cls_bytes[KC_COUNT] = {0};
   int64_t cls_launches[KC_COUNT] = {0};
   void* model = nullptr;  // Model* (model.cu)
+  unsigned int* splitk_tickets = nullptr;  // 64K zeroed counters (gemm_tc split-K tile tickets)
   // SDB_DEBUG_SYNC=1: synchronise after every launch and report the failing op (bring-up aid)
   bool debug_sync = false;
   std::string dbg_label;

@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing of the sampling path: one process per GPU, images are independent units.
+
+  * image i of a job runs on rank  i mod world  (shard_images)
+  * weights: rank 0 owns the fp32 master arena; ONE broadcast ships it at init (broadcast_arena); there is no
+    collective on the sampling path itself
+  * results: every rank keeps its own images; gather_images concatenates them in image order on rank 0.
+
+Works with any torch.distributed backend: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_images(n_images: int, rank: int, world: int) -> list[int]:
+    """Indices of the images this rank samples (round-robin, identical on every rank)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_images, world))
+
+
+def image_seed(base_seed: int, image_index: int) -> int:
+    """Per-image RNG stream (seed = 1234 + image index) — independent of the rank count."""
+    return base_seed + image_index
+
+
+def broadcast_arena(arena, src: int = 0):
+    """In-place broadcast of the flat fp32 weight arena (a torch tensor view of sdb_weight_arena)."""
+    import torch.distributed as dist
+    dist.broadcast(arena, src)
+    return arena
+
+
+def gather_images(local_images: np.ndarray, n_images: int, rank: int, world: int):
+    """local_images [k,H,W,3] uint8 for shard_images(...) -> [n_images,H,W,3] on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    k_max = (n_images + world - 1) // world
+    h, w, c = local_images.shape[1:]
+    pad = torch.zeros((k_max, h, w, c), dtype=torch.uint8)
+    pad[: local_images.shape[0]] = torch.from_numpy(local_images)
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0)
+    if rank != 0:
+        return None
+    out = np.zeros((n_images, h, w, c), np.uint8)
+    for r in range(world):
+        idx = shard_images(n_images, r, world)
+        out[idx] = bufs[r][: len(idx)].numpy()
+    return out
