@@ -66,11 +66,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int q0 = blockIdx.x * (128 * NG);
   const int h = blockIdx.y;
   const int s = blockIdx.z;
-  const int kvlen = p.kvlen ? p.kvlen[s] : p.Nk;
-  const int T = (kvlen + 127) / 128;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -101,6 +100,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int kvlen = p.kvlen ? p.kvlen[s] : p.Nk;
+  const int T = (kvlen + 127) / 128;
   // columns: S_g at g*128 ; O_g at NG*128 + g*DPAD
 
   if (warp == 0) {
@@ -305,8 +307,7 @@ static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
     attr = true;
   }
   dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
-  attention_kernel<DPAD, NG><<<grid, 64 + 128 * NG, smem, st>>>(mq, mk, mv, p);
-  SDB_CUDA(cudaGetLastError());
+  launch_k(attention_kernel<DPAD, NG>, grid, dim3(64 + 128 * NG), (size_t)smem, st, mq, mk, mv, p);
 }
 
 void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,

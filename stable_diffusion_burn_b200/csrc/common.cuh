@@ -5,8 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <stdexcept>
+#include <utility>
 
 namespace sdb {
 
@@ -30,8 +32,33 @@ struct Error : std::runtime_error {
                          __FILE__ + ":" + std::to_string(__LINE__));                    \
   } while (0)
 
+// --------------------------------------------------------------------------- launches
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start (launch latency, CTA
+// scheduling, its prologue up to pdl_wait()) while its predecessor on the stream is still draining.
+extern bool g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 // --------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+
+// PDL device side: let the next kernel of the stream start launching, then wait until everything the
+// previous kernel wrote is visible. Harmless when the launch carried no PDL attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

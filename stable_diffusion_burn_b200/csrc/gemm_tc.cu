@@ -43,6 +43,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel of the stream may begin its own prologue
 
   // ---- tile coordinates
   int mt = blockIdx.x;
@@ -85,6 +86,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -231,38 +233,47 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have published their part of the tile
-      uint32_t* flag = reinterpret_cast<uint32_t*>(tile_flag);
+      // Tile-level rendezvous of the split_k CTAs (all co-resident: run_gemm keeps ctas*split within one wave), then
+      // every CTA folds its own slice of the tile rows in z order (deterministic) and runs the epilogue on it.
+      unsigned int* tk = p.tickets + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
       if (warp == 2 && lane == 0) {
-        unsigned int* tk = p.tickets + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned int old = atomicAdd(tk, 1u);
-        const bool last = old == (unsigned)(p.split_k - 1);
-        if (last) *tk = 0u;  // self-cleaning: the buffer is all zero again for the next launch
-        *flag = last ? 1u : 0u;
+        atomicAdd(tk, 1u);
+        const long long t0 = clock64();
+        while (atomicAdd(tk, 0u) < (unsigned)p.split_k) {
+          __nanosleep(32);
+          if (clock64() - t0 > 4000000000ll) __trap();
+        }
+        __threadfence();
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (*flag) {
-        __threadfence();
-#pragma unroll 1
-        for (int c = half * 32; c < BN; c += 64) {
-          const int col = col0 + c + cq;
-          const bool col_ok = col < p.N;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + sub;
-            const long long mr = __shfl_sync(0xffffffffu, m, rr);
-            const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
-            const int pnr = __shfl_sync(0xffffffffu, pn, rr);
-            if (okr && col_ok) {
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int z = 0; z < p.split_k; ++z) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + mr) * p.N + col));
-                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-              }
-              finish(acc, mr, pnr, col, bv);
+      {
+        const int rows_per = (BM + p.split_k - 1) / p.split_k;
+        const int r0 = blockIdx.z * rows_per, r1 = min(BM, r0 + rows_per);
+        constexpr int C4 = BN / 4;
+        const int te = threadIdx.x - 64;
+        for (int idx = te; idx < (r1 - r0) * C4; idx += 256) {
+          const int rl = r0 + idx / C4;
+          const int col = col0 + (idx % C4) * 4;
+          const int qw = w0 + rl % p.TW, qh = h0 + (rl / p.TW) % p.TH, qn = n0 + rl / (p.TW * p.TH);
+          if (qw < p.W && qh < p.H && qn < p.nimg && col < p.N) {
+            const long long mr = ((long long)qn * p.OH + (long long)qh * p.os + p.oa) * p.OW + (long long)qw * p.os + p.ob;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < p.split_k; ++z) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + mr) * p.N + col));
+              acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
+            finish(acc, mr, qn, col, bv);
           }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        // last CTA to finish resets both counters: the buffer is all zero again for the next launch
+        if (atomicAdd(tk + 1, 1u) == (unsigned)(p.split_k - 1)) {
+          tk[0] = 0u;
+          tk[1] = 0u;
         }
       }
     } else if (p.geglu) {
@@ -420,10 +431,12 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid, cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 2 : 1;
   SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES>, maps, p));
 }
 

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
                                                        const float* __restrict__ x1, int C1, int HW, int pix_per_cta,
                                                        double* __restrict__ sums, float* __restrict__ partials,
                                                        unsigned int* __restrict__ tickets) {
+  pdl_enter();
   __shared__ float s_pair[2][1280];  // per channel-pair (sum, sumsq), C <= 2560
   __shared__ bool s_last;
   const int n = blockIdx.y;
@@ -106,7 +107,7 @@ void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, in
   int pix = (int)((((long long)HW * n) + 591) / 592);
   if (pix < 16) pix = 16;
   dim3 grid(ceil_div(HW, pix), n);
-  gn_stats_kernel<<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, pix, sums, partials, tickets);
+  launch_k(gn_stats_kernel, grid, dim3(256), 0, st, x0, C0, x1, C1, HW, pix, sums, partials, tickets);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -129,6 +130,7 @@ prep_operand_kernel(const float* __restrict__ x0, int C0, const float* __restric
                     int pix_per_cta, int mode, const double* __restrict__ sums, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, __half* __restrict__ out_hi,
                     __half* __restrict__ out_lo) {
+  pdl_enter();
   extern __shared__ float s_aff[];  // scale[C], shift[C]
   const int n = blockIdx.y;
   const int C = C0 + C1, HW = H * W;
@@ -187,7 +189,7 @@ void prep_operand_launch(const float* x0, int C0, const float* x1, int C1, int n
   if (pix < 8) pix = 8;
   dim3 grid(ceil_div(HW, pix), n);
   const size_t smem = (mode & PREP_NORM) ? (size_t)2 * C * sizeof(float) : 0;
-  prep_operand_kernel<<<grid, 256, smem, st>>>(x0, C0, x1, C1, H, W, pix, mode, sums, gamma, beta, eps, out.hi, out.lo);
+  launch_k(prep_operand_kernel, grid, dim3(256), smem, st, x0, C0, x1, C1, H, W, pix, mode, sums, gamma, beta, eps, out.hi, out.lo);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -201,6 +203,7 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
                 int silu, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, double* __restrict__ sums,
                 float* __restrict__ partials, unsigned int* __restrict__ tickets, unsigned int* __restrict__ flags) {
+  pdl_enter();
   extern __shared__ float s_dyn[];  // scale[C], shift[C]
   __shared__ float s_pair[2][1280];
   __shared__ bool s_last;
@@ -271,7 +274,11 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
   }
   // ---- wait for the image's statistics
   if (threadIdx.x == 0) {
-    while (atomicAdd(&flags[n], 0u) == 0u) __nanosleep(100);
+    const long long t0 = clock64();
+    while (atomicAdd(&flags[n], 0u) == 0u) {
+      __nanosleep(100);
+      if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost CTA becomes a launch failure, not a hung GPU
+    }
     __threadfence();
   }
   __syncthreads();
@@ -327,8 +334,8 @@ void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, in
   const int pix = gn_fused_pix(n, HW);
   dim3 grid(ceil_div(HW, pix), n);
   SDB_CHECK((long long)grid.x * grid.y <= 592, "fused GroupNorm grid must stay co-resident");
-  gn_fused_kernel<<<grid, 256, (size_t)2 * C * sizeof(float), st>>>(x0, C0, x1, C1, H, W, pix, silu, gamma, beta, eps, out.hi,
-                                                                     out.lo, sums, partials, tickets, flags);
+  launch_k(gn_fused_kernel, grid, dim3(256), (size_t)2 * C * sizeof(float), st, x0, C0, x1, C1, H, W, pix, silu, gamma, beta, eps, out.hi,
+           out.lo, sums, partials, tickets, flags);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                  float* __restrict__ out_f32) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -417,15 +425,16 @@ void layernorm_launch(const float* x, int rows, int C, const float* gamma, const
   SDB_CHECK(C % 8 == 0 && C <= 1280, "LayerNorm width");
   const int grid = ceil_div(rows, 8);
   if (C <= 512)
-    layernorm_kernel<2><<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
+    launch_k(layernorm_kernel<2>, dim3(grid), dim3(256), 0, st, x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
   else
-    layernorm_kernel<5><<<grid, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
+    launch_k(layernorm_kernel<5>, dim3(grid), dim3(256), 0, st, x, rows, C, gamma, beta, eps, out.hi, out.lo, out_f32);
   SDB_CUDA(cudaGetLastError());
 }
 
 // ============================================================ conversions
 __global__ void convert_f16_kernel(const float* __restrict__ x, long long count8, __half* __restrict__ hi,
                                    __half* __restrict__ lo) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count8; i += (long long)gridDim.x * blockDim.x) {
     float4 a = *reinterpret_cast<const float4*>(x + i * 8);
     float4 b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
@@ -481,6 +490,7 @@ __global__ void __launch_bounds__(256)
 conv3x3_cin4_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w, const float* __restrict__ b,
                     int Cout, const float* __restrict__ pre_w, const float* __restrict__ pre_b, float pre_scale,
                     float* __restrict__ y) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* s_w = sm;                  // [36][Cout]
   float* s_in = sm + 36 * Cout;     // [PIX][36]
@@ -533,7 +543,7 @@ void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* 
     attr = true;
   }
   dim3 grid(ceil_div(H * W, 32), n);
-  conv3x3_cin4_kernel<<<grid, 256, smem, st>>>(x_nchw, H, W, w, b, Cout, pre_w, pre_b, pre_scale, y);
+  launch_k(conv3x3_cin4_kernel, grid, dim3(256), smem, st, x_nchw, H, W, w, b, Cout, pre_w, pre_b, pre_scale, y);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -544,6 +554,7 @@ __global__ void __launch_bounds__(256)
 conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, const double* __restrict__ sums,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                           const float* __restrict__ wp, const float* __restrict__ b, float* __restrict__ y) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* s_scale = sm;      // [C]
   float* s_shift = sm + C;  // [C]
@@ -601,9 +612,9 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
   if (gx > 148 * 8) gx = 148 * 8;
   dim3 grid(gx, n);
   if (Cout == 4)
-    conv3x3_small_cout_kernel<4><<<grid, 256, smem, st>>>(x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
+    launch_k(conv3x3_small_cout_kernel<4>, grid, dim3(256), smem, st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
   else if (Cout == 3)
-    conv3x3_small_cout_kernel<3><<<grid, 256, smem, st>>>(x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
+    launch_k(conv3x3_small_cout_kernel<3>, grid, dim3(256), smem, st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
   else
     throw Error("conv3x3_small_cout: Cout must be 3 or 4");
   SDB_CUDA(cudaGetLastError());
@@ -615,6 +626,7 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 __global__ void __launch_bounds__(256)
 gemv_kernel(const float* __restrict__ x, const int* __restrict__ t_dev, const float* __restrict__ W,
             const float* __restrict__ b, int K, int N, int silu, float* __restrict__ y) {
+  pdl_enter();
   __shared__ float s_part[8][32];
   __shared__ float s_x[1280];
   if (t_dev) {
@@ -646,14 +658,14 @@ gemv_kernel(const float* __restrict__ x, const int* __restrict__ t_dev, const fl
 }
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st) {
   SDB_CHECK(K <= 1280, "gemv K");
-  gemv_kernel<<<ceil_div(N, 32), 256, 0, st>>>(x, nullptr, W, b, K, N, 0, y);
+  launch_k(gemv_kernel, dim3(ceil_div(N, 32)), dim3(256), 0, st, x, (const int*)nullptr, W, b, K, N, 0, y);
   SDB_CUDA(cudaGetLastError());
 }
 // emb_silu = silu(lin2(silu(lin1(timestep_embedding(t)))))  — two multi-CTA GEMVs (was one CTA: 140 us)
 void time_embed_launch(const int* t, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
                        float* emb_silu, cudaStream_t st) {
-  gemv_kernel<<<ceil_div(1280, 32), 256, 0, st>>>(nullptr, t, w1, b1, 320, 1280, 1, hidden);
-  gemv_kernel<<<ceil_div(1280, 32), 256, 0, st>>>(hidden, nullptr, w2, b2, 1280, 1280, 1, emb_silu);
+  launch_k(gemv_kernel, dim3(40), dim3(256), 0, st, (const float*)nullptr, t, w1, b1, 320, 1280, 1, hidden);
+  launch_k(gemv_kernel, dim3(40), dim3(256), 0, st, (const float*)hidden, (const int*)nullptr, w2, b2, 1280, 1280, 1, emb_silu);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -661,6 +673,7 @@ void time_embed_launch(const int* t, const float* w1, const float* b1, const flo
 __global__ void cfg_ddim_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ lat,
                                 long long count, float scale, float sqrt_1m_at, float sqrt_at, float sqrt_aprev,
                                 float dir_coef) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float u = eu[i], c = ec[i];
     const float pred = u + (c - u) * scale;               // stablediffusion/mod.rs:190-191
@@ -674,11 +687,12 @@ void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long
                      float sqrt_one_minus_at, float sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st) {
   int grid = (int)((count + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  cfg_ddim_kernel<<<grid, 256, 0, st>>>(eps_u, eps_c, latent, count, scale, sqrt_one_minus_at, sqrt_at, sqrt_aprev, dir_coef);
+  launch_k(cfg_ddim_kernel, dim3(grid), dim3(256), 0, st, eps_u, eps_c, latent, count, scale, sqrt_one_minus_at, sqrt_at, sqrt_aprev, dir_coef);
   SDB_CUDA(cudaGetLastError());
 }
 
 __global__ void to_rgb8_kernel(const float* __restrict__ img, int HW, long long total, uint8_t* __restrict__ rgb) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % 3);
     const long long r = i / 3;

@@ -9,6 +9,8 @@
 
 namespace sdb {
 
+bool g_pdl_enabled = true;
+
 // ------------------------------------------------------------------ arena
 void Arena::init(size_t bytes) {
   SDB_CUDA(cudaMalloc(&base, bytes));
@@ -338,7 +340,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     if (split > 1) {
       const size_t need = (size_t)split * (size_t)Mtot * w.N * sizeof(float);
       p.ws = reinterpret_cast<float*>(c.work.alloc(need));
-      SDB_CHECK((long long)m_tiles * n_tiles <= 65536, "split-K ticket buffer");
+      SDB_CHECK((long long)m_tiles * n_tiles * 2 <= 65536, "split-K ticket buffer");
+      SDB_CHECK((long long)m_tiles * n_tiles * split <= 148, "split-K CTAs must be co-resident");
       p.tickets = c.splitk_tickets;
     }
     {
