@@ -35,6 +35,15 @@ def peaks():
         return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
 
 
+def gemm_traffic_per_launch():
+    """DRAM bytes per gemm_tc launch from the committed ncu capture (profiles/r1_gemm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -295,7 +304,7 @@ def main():
         ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/linear layers of one sample_image)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "peak_source": pk["src"] + " bf16 cuBLAS sustained (same tensor rate as fp16)",
-                "traffic": None, "launches": g["launches"], "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]),
+                "traffic": gemm_traffic_per_launch(), "launches": g["launches"], "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]),
                 "algorithmic_tflop_per_step": g["flops"] / 1e12, "issued_tflop_per_step": g["bytes"] / 1e12,
                 "share_of_step": g["ms"] / tot_ms if tot_ms else None,
                 "whole_image_tflops": value / world * FLOP_PER_IMAGE / 1e12 if args.size == 512 and args.ddim_steps == 20 else None}

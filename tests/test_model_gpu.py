@@ -155,3 +155,32 @@ def test_error_paths(sd):
         sd.unet_forward(np.zeros((1, 4, 16, 16), np.float32), 1, synth.kat_context())  # deepest level would have 4 tokens
     with pytest.raises(Exception):
         sd.unet_forward(np.zeros((1, 4, 12, 12), np.float32), 1, synth.kat_context())  # not a multiple of 8
+
+
+# ------------------------------------------------------------------ BASELINE configs 3-5 as parity cases
+def test_unet_768px_golden(sd):
+    """config C4 geometry: 96x96 latent (768x768 px): 9216 / 2304 / 576 / 144 tokens per level, non power-of-two tiles."""
+    g = np.load(os.path.join(GOLD, "unet_768px.npz"))
+    out = sd.unet_forward(synth.make_latent(1, 96, 96, seed=96), 777, synth.make_context(1, 9, seed=96))
+    e2, em = rel(out, g["out"]), relmax(out, g["out"])
+    print(f"unet 96x96: rel L2 {e2:.3e} max/max {em:.3e}")
+    assert e2 < UNET_TOL and em < UNET_TOL
+
+
+def test_batch_invariance(sd):
+    """configs C3/C5 run batches of 8 per GPU: an image must not depend on what else is in its batch."""
+    ctx_t = synth.make_context(8, 11, seed=41); unc = synth.make_context(1, 2, seed=99)[0]; init = synth.make_latent(8, 32, 32, seed=51)
+    full = sd.sample_latent(ctx_t, unc, 7.5, 2, init_latent=init)
+    for i in (0, 5):
+        one = sd.sample_latent(ctx_t[i:i + 1], unc, 7.5, 2, init_latent=init[i:i + 1])
+        e = rel(full[i:i + 1], one)
+        print(f"batch invariance image {i}: rel L2 {e:.3e}")
+        assert e < 5e-4  # tile shapes / split-K differ with the batch size -> not bit-exact, but fp32-class
+
+
+def test_decode_batch8(sd):
+    lat = synth.make_latent(8, 16, 16, seed=61)
+    imgs = sd.decode_latent(lat)
+    one = sd.decode_latent(lat[6:7])
+    assert imgs.shape == (8, 3, 128, 128) and np.isfinite(imgs).all()
+    assert rel(imgs[6:7], one) < 5e-4
