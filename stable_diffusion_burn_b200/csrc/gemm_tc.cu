@@ -34,7 +34,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using L = StageLayout<BN, PASSES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
@@ -160,7 +160,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     // Each thread owns one accumulator row in TMEM (warp w may touch lanes 32*(w%4)..+31); the two warps that
     // share a lane quarter split the 32-column chunks between them. A row-per-thread store pattern would touch 32
     // cache lines per instruction, so every 32x32 block is transposed through shared memory (the pipeline stages
-    // are idle by now) and written/read as 4 rows x 128 contiguous bytes per warp instruction.
+    // are idle by now; rows padded to 144 B keep both the 128-bit writes and reads bank-conflict free) and
+    // written/read as 4 rows x 128 contiguous bytes per warp instruction.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which half of the column chunks this warp owns
     const int r = q * 32 + lane;        // accumulator row
@@ -168,35 +169,50 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int phh = h0 + (r / p.TW) % p.TH;
     const int pn = n0 + r / (p.TW * p.TH);
     const int row_ok = ((pw < p.W) && (phh < p.H) && (pn < p.nimg)) ? 1 : 0;
-    const long long m = ((long long)pn * p.OH + (long long)phh * p.os + p.oa) * p.OW + (long long)pw * p.os + p.ob;
+    // output row index (< 2^31 rows); -1 marks a row outside the tensor
+    const int m = row_ok ? ((pn * p.OH + phh * p.os + p.oa) * p.OW + pw * p.os + p.ob) : -1;
 
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (2 * 32 * 33);  // two 32x33 fp32 tiles per warp
-    float* tile2 = tile + 32 * 33;
+    constexpr uint32_t TROW = 144;                                   // padded row pitch of the staging tile (bytes)
+    const uint32_t tile_s = smem_u32(smem) + (warp - 2) * (32 * TROW);  // one 32-row tile per warp (36.9 KB in all)
+    const uint32_t tile2_s = tile_s + 8 * 32 * TROW;                     // second bank, GEGLU only (x | gate)
+    static_assert(STAGES * L::BYTES >= 2 * 8 * 32 * 144 || STAGES * L::BYTES >= 8 * 32 * 144, "staging tiles must fit in the pipeline stages");
     const int sub = lane >> 3;          // row within a group of 4
     const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
 
-    auto stage = [&](float* t, const uint32_t (&v)[32]) {
+    auto stage = [&](uint32_t t, const uint32_t (&v)[32]) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[lane * 33 + j] = __uint_as_float(v[j]);
+      for (int k = 0; k < 8; ++k)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t + lane * TROW + k * 16), "r"(v[4 * k]),
+                     "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3])
+                     : "memory");
+    };
+    auto unstage = [&](uint32_t t, int rr) {
+      float4 f;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                   : "r"(t + rr * TROW + cq * 4)
+                   : "memory");
+      return f;
     };
     // bias / time-embedding row / residual / fp32 + fp16(hi,lo) stores for 4 consecutive columns of one output row
-    auto finish = [&](float4 f, long long mr, int pnr, int col, const float4& bv) {
+    auto finish = [&](float4 f, int mr, int pnr, int col, const float4& bv) {
       f.x += bv.x, f.y += bv.y, f.z += bv.z, f.w += bv.w;
       if (p.rowbias) {
-        const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (long long)pnr * p.N + col);
+        const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)pnr * p.N + col);
         f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
       }
+      const size_t o32 = (size_t)mr * p.ldc + col;
       if (p.residual) {
-        const float4 b = *reinterpret_cast<const float4*>(p.residual + mr * p.ldc + col);
+        const float4 b = *reinterpret_cast<const float4*>(p.residual + o32);
         f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
       }
-      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + mr * p.ldc + col) = f;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o32) = f;
       if (p.out_f16) {
         __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
-        const long long o = mr * p.ldc16 + col;
+        const size_t o = (size_t)mr * p.ldc16 + col;
         *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
         if (p.out_f16_lo) {
           const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
@@ -207,27 +223,22 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     };
 
     if (p.split_k > 1) {
-      // raw partial sums -> workspace [split][M][N]; the LAST CTA of this tile (ticket) folds the splits in z order
-      // (deterministic) and runs the epilogue — no separate reduction launch.
-      const long long Mtot = (long long)p.nimg * p.OH * p.OW;
-      float* wsbase = p.ws + (long long)blockIdx.z * Mtot * p.N;
+      // raw partial sums -> workspace [split][M][N]
+      const size_t Mtot = (size_t)p.nimg * p.OH * p.OW;
+      float* wsbase = p.ws + (size_t)blockIdx.z * Mtot * p.N;
 #pragma unroll 1
       for (int c = half * 32; c < BN; c += 64) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        stage(tile, v);
+        stage(tile_s, v);
         __syncwarp();
         const int col = col0 + c + cq;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub;
-          const long long mr = __shfl_sync(0xffffffffu, m, rr);
-          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
-          if (okr && col < p.N) {
-            const float* t = tile + rr * 33 + cq;
-            __stcg(reinterpret_cast<float4*>(wsbase + mr * p.N + col), make_float4(t[0], t[1], t[2], t[3]));
-          }
+          const int mr = __shfl_sync(0xffffffffu, m, rr);
+          if (mr >= 0 && col < p.N) __stcg(reinterpret_cast<float4*>(wsbase + (size_t)mr * p.N + col), unstage(tile_s, rr));
         }
         __syncwarp();
       }
@@ -256,10 +267,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const int col = col0 + (idx % C4) * 4;
           const int qw = w0 + rl % p.TW, qh = h0 + (rl / p.TW) % p.TH, qn = n0 + rl / (p.TW * p.TH);
           if (qw < p.W && qh < p.H && qn < p.nimg && col < p.N) {
-            const long long mr = ((long long)qn * p.OH + (long long)qh * p.os + p.oa) * p.OW + (long long)qw * p.os + p.ob;
+            const int mr = (qn * p.OH + qh * p.os + p.oa) * p.OW + qw * p.os + p.ob;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int z = 0; z < p.split_k; ++z) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + mr) * p.N + col));
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)z * Mtot + mr) * p.N + col));
               acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             }
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -285,27 +296,25 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        stage(tile, v);
+        stage(tile_s, v);
         tmem_ld32(trow + HB + c, v);
         tmem_ld_wait();
-        stage(tile2, v);
+        stage(tile2_s, v);
         __syncwarp();
         const float4 bx = *reinterpret_cast<const float4*>(p.bias + col0 + c + cq);
         const float4 bg = *reinterpret_cast<const float4*>(p.bias + col0 + HB + c + cq);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub;
-          const long long mr = __shfl_sync(0xffffffffu, m, rr);
-          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
-          if (okr && col0 + c < p.N) {
-            const float* tx = tile + rr * 33 + cq;
-            const float* tg = tile2 + rr * 33 + cq;
-            const float y0 = (tx[0] + bx.x) * gelu_erf_fast(tg[0] + bg.x);
-            const float y1 = (tx[1] + bx.y) * gelu_erf_fast(tg[1] + bg.y);
-            const float y2 = (tx[2] + bx.z) * gelu_erf_fast(tg[2] + bg.z);
-            const float y3 = (tx[3] + bx.w) * gelu_erf_fast(tg[3] + bg.w);
+          const int mr = __shfl_sync(0xffffffffu, m, rr);
+          if (mr >= 0) {
+            const float4 tx = unstage(tile_s, rr), tg = unstage(tile2_s, rr);
+            const float y0 = (tx.x + bx.x) * gelu_erf_fast(tg.x + bg.x);
+            const float y1 = (tx.y + bx.y) * gelu_erf_fast(tg.y + bg.y);
+            const float y2 = (tx.z + bx.z) * gelu_erf_fast(tg.z + bg.z);
+            const float y3 = (tx.w + bx.w) * gelu_erf_fast(tg.w + bg.w);
             __half2 h[2] = {__floats2half2_rn(y0, y1), __floats2half2_rn(y2, y3)};
-            const long long o = mr * p.ldc16 + ocol0 + c + cq;
+            const size_t o = (size_t)mr * p.ldc16 + ocol0 + c + cq;
             *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
             if (p.out_f16_lo) {
               const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
@@ -322,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
-        stage(tile, v);
+        stage(tile_s, v);
         __syncwarp();
         const int col = col0 + c + cq;
         const bool col_ok = col < p.N;
@@ -331,13 +340,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub;
-          const long long mr = __shfl_sync(0xffffffffu, m, rr);
-          const int okr = __shfl_sync(0xffffffffu, row_ok, rr);
-          const int pnr = __shfl_sync(0xffffffffu, pn, rr);
-          if (okr && col_ok) {
-            const float* t = tile + rr * 33 + cq;
-            finish(make_float4(t[0], t[1], t[2], t[3]), mr, pnr, col, bv);
-          }
+          const int mr = __shfl_sync(0xffffffffu, m, rr);
+          const int pnr = p.rowbias ? __shfl_sync(0xffffffffu, pn, rr) : 0;
+          if (mr >= 0 && col_ok) finish(unstage(tile_s, rr), mr, pnr, col, bv);
         }
         __syncwarp();
       }
