@@ -197,6 +197,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout must carry exactly one JSON line: NCCL_DEBUG=VERSION would print the NCCL banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = _lib.Context(local)
