@@ -169,7 +169,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdb200")
     ap.add_argument("--batch", type=int, default=1, help="images per rank per step (BASELINE configs[1] = 1; configs[4] = 8)")
