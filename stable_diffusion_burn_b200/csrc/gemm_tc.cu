@@ -20,18 +20,22 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;  // fp16 elements per k chunk = 128 bytes = one swizzle row
 static constexpr int A_TILE_BYTES = BM * BK * 2;
 
-template <int BN, int PASSES>
+// CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cluster of 2 along M) runs ONE tcgen05.mma.cta_group::2
+// of shape 256 x BN per k-step: each CTA stages its own 128 A rows and only HALF of the weight tile, so the operand
+// bytes per FLOP that cross the L2->SM fabric drop by 25-45 % (the bound measured in profiles/r1_gemm_tc_ncu_full.md).
+template <int BN, int PASSES, int CG = 1>
 struct StageLayout {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;
   static constexpr int A_TILES = PASSES >= 2 ? 2 : 1;
   static constexpr int B_TILES = PASSES >= 3 ? 2 : 1;
   static constexpr int BYTES = A_TILES * A_TILE_BYTES + B_TILES * B_TILE_BYTES;
 };
 
-template <int BN, int PASSES, int STAGES>
+template <int BN, int PASSES, int STAGES, int CG>
 __global__ void __launch_bounds__(320, 2)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  using L = StageLayout<BN, PASSES>;
+  using L = StageLayout<BN, PASSES, CG>;
+  constexpr bool TWO = CG == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -59,12 +63,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int it_begin = blockIdx.z * per_split;
   const int it_end = min(total_iters, it_begin + per_split);
 
-  const bool paired = p.cluster == 2;
-  const uint32_t crank = paired ? cluster_ctarank() : 0;
+  const uint32_t crank = TWO ? cluster_ctarank() : 0;
+  const bool leader = crank == 0;  // the CTA that issues the pair's MMAs and owns the "full" barriers
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], paired ? 2 : 1);  // paired: both consumers must release a stage (either CTA writes into both)
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
@@ -76,12 +80,17 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   }
   constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // power of two >= BN
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc2(tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  if (paired)
-    cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast into its smem
+  if (TWO)
+    cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   else
     __syncthreads();
   tc_fence_after();
@@ -95,25 +104,26 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       uint32_t ph = 0;
       for (int it = it_begin; it < it_end; ++it) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], L::BYTES);
+        if (leader) mbar_expect_tx(&full_bar[s], L::BYTES * CG);  // both CTAs' loads report to the leader's barrier
         uint8_t* st = smem + s * L::BYTES;
         const int tap = it / p.kc;
         const int cc = it - tap * p.kc;
         const int src = cc >= p.kc0 ? 1 : 0;
         const int c0 = (cc - (src ? p.kc0 : 0)) * BK;
         const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
-        tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
-        if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
         uint8_t* sb = st + L::A_TILES * A_TILE_BYTES;
-        if (!paired) {
+        if (!TWO) {
+          tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
+          if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
           tma_load_2d(sb, &maps.b[0], &full_bar[s], it * BK, col0);
           if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &maps.b[1], &full_bar[s], it * BK, col0);
         } else {
-          // this CTA fetches rows [crank*BN/2, +BN/2) of the weight tile for BOTH CTAs of the pair
-          constexpr int HALF = (BN / 2) * BK * 2;
-          tma_load_2d_mc(sb + crank * HALF, &maps.b[0], &full_bar[s], it * BK, col0 + crank * (BN / 2), 0x3);
-          if (PASSES >= 3)
-            tma_load_2d_mc(sb + L::B_TILE_BYTES + crank * HALF, &maps.b[1], &full_bar[s], it * BK, col0 + crank * (BN / 2), 0x3);
+          // own 128 A rows + rows [crank*BN/2, +BN/2) of the weight tile, into this CTA's smem
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+          tma_load_5d_2sm(st, &maps.a[src][0], fb, c0, cw, ch, cp, n0);
+          if (PASSES >= 2) tma_load_5d_2sm(st + A_TILE_BYTES, &maps.a[src][1], fb, c0, cw, ch, cp, n0);
+          tma_load_2d_2sm(sb, &maps.b[0], fb, it * BK, col0 + crank * (BN / 2));
+          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &maps.b[1], fb, it * BK, col0 + crank * (BN / 2));
         }
         if (++s == STAGES) {
           s = 0;
@@ -122,11 +132,11 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    // ===================================================== MMA issuer (pair leader only when CG = 2)
+    constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = it_begin; it < it_end; ++it) {
+    for (int it = it_begin; leader && it < it_end; ++it) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
@@ -139,15 +149,24 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const uint32_t koff = k * 32;  // 16 fp16 = 32 bytes inside the 128B swizzle row
           const uint64_t da = make_sdesc_sw128(a_hi + koff);
           const uint64_t db = make_sdesc_sw128(b_hi + koff);
-          umma_f16(tmem_base, da, db, idesc, (it > it_begin || k > 0) ? 1u : 0u);
-          if (PASSES >= 2) umma_f16(tmem_base, make_sdesc_sw128(a_lo + koff), db, idesc, 1u);
-          if (PASSES >= 3) umma_f16(tmem_base, da, make_sdesc_sw128(b_lo + koff), idesc, 1u);
+          const uint32_t acc = (it > it_begin || k > 0) ? 1u : 0u;
+          if (TWO) {
+            umma_f16_2sm(tmem_base, da, db, idesc, acc);
+            if (PASSES >= 2) umma_f16_2sm(tmem_base, make_sdesc_sw128(a_lo + koff), db, idesc, 1u);
+            if (PASSES >= 3) umma_f16_2sm(tmem_base, da, make_sdesc_sw128(b_lo + koff), idesc, 1u);
+          } else {
+            umma_f16(tmem_base, da, db, idesc, acc);
+            if (PASSES >= 2) umma_f16(tmem_base, make_sdesc_sw128(a_lo + koff), db, idesc, 1u);
+            if (PASSES >= 3) umma_f16(tmem_base, da, make_sdesc_sw128(b_lo + koff), idesc, 1u);
+          }
         }
-        if (paired)
-          umma_commit_mc(&empty_bar[s], 0x3);            // release the slot in both CTAs of the pair
-        else
+        if (TWO) {
+          umma_commit_2sm(&empty_bar[s], 0x3);                     // release the slot in both CTAs of the pair
+          if (it == it_end - 1) umma_commit_2sm(accum_bar, 0x3);   // both epilogues may start
+        } else {
           umma_commit(&empty_bar[s]);                    // frees the smem slot when these MMAs retire
-        if (it == it_end - 1) umma_commit(accum_bar);    // accumulator complete
+          if (it == it_end - 1) umma_commit(accum_bar);  // accumulator complete
+        }
       }
       __syncwarp();
       if (++s == STAGES) {
@@ -178,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     constexpr uint32_t TROW = 144;                                   // padded row pitch of the staging tile (bytes)
     const uint32_t tile_s = smem_u32(smem) + (warp - 2) * (32 * TROW);  // one 32-row tile per warp (36.9 KB in all)
     const uint32_t tile2_s = tile_s + 8 * 32 * TROW;                     // second bank, GEGLU only (x | gate)
-    static_assert(STAGES * L::BYTES >= 2 * 8 * 32 * 144 || STAGES * L::BYTES >= 8 * 32 * 144, "staging tiles must fit in the pipeline stages");
+
     const int sub = lane >> 3;          // row within a group of 4
     const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
 
@@ -350,13 +369,16 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     tc_fence_before();
   }
 
-  if (paired)
-    cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers
+  if (TWO)
+    cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers / read its smem
   else
     __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO)
+      tmem_dealloc2(tmem_base, TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -409,27 +431,28 @@ void splitk_reduce_launch(const GemmParams& p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------ launcher
-template <int BN, int PASSES>
+template <int BN, int PASSES, int CG>
 constexpr int pick_stages() {
   // as many stages as fit in ~200 KB, capped at 8
-  constexpr int per = StageLayout<BN, PASSES>::BYTES;
+  constexpr int per = StageLayout<BN, PASSES, CG>::BYTES;
   constexpr int n = (200 * 1024) / per;
   return n > 8 ? 8 : n;
 }
-template <int BN, int PASSES>
+template <int BN, int PASSES, int CG>
 constexpr int pick_stages_half() {
   // configuration that lets two CTAs share one SM (<= ~110 KB each)
-  constexpr int per = StageLayout<BN, PASSES>::BYTES;
+  constexpr int per = StageLayout<BN, PASSES, CG>::BYTES;
   constexpr int n = (104 * 1024) / per;
   return n > 4 ? 4 : (n < 2 ? 2 : n);
 }
 
-template <int BN, int PASSES, int STAGES>
+template <int BN, int PASSES, int STAGES, int CG>
 static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * StageLayout<BN, PASSES>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * StageLayout<BN, PASSES, CG>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 8 * 32 * 144, "epilogue staging tiles must fit in the stages");
   static bool attr_set = false;
   if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
@@ -442,23 +465,32 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 2 : 1;
-  SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES>, maps, p));
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES, CG>, maps, p));
 }
 
+template <int BN, int PASSES, int CG>
+static void launch_cg(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+  const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * p.split_k;
+  constexpr int SH = pick_stages_half<BN, PASSES, CG>();
+  constexpr bool half_ok = SH * StageLayout<BN, PASSES, CG>::BYTES <= 104 * 1024 && SH * StageLayout<BN, PASSES, CG>::BYTES >= 8 * 32 * 144 * 2;
+  // many short tiles: two co-resident CTAs per SM overlap one tile's epilogue with the other's mainloop
+  if (half_ok && ctas >= 2 * 148)
+    launch_inst<BN, PASSES, half_ok ? SH : pick_stages<BN, PASSES, CG>(), CG>(maps, p, stream);
+  else
+    launch_inst<BN, PASSES, pick_stages<BN, PASSES, CG>(), CG>(maps, p, stream);
+}
 template <int BN, int PASSES>
 static void launch_bn(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
-  const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * p.split_k;
-  // many short tiles: two co-resident CTAs per SM overlap one tile's epilogue with the other's mainloop
-  if (p.cluster == 1 && ctas >= 2 * 148 && pick_stages_half<BN, PASSES>() * StageLayout<BN, PASSES>::BYTES <= 104 * 1024)
-    launch_inst<BN, PASSES, pick_stages_half<BN, PASSES>()>(maps, p, stream);
+  if (p.cluster == 2)
+    launch_cg<BN, PASSES, 2>(maps, p, stream);
   else
-    launch_inst<BN, PASSES, pick_stages<BN, PASSES>()>(maps, p, stream);
+    launch_cg<BN, PASSES, 1>(maps, p, stream);
 }
 
 void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream) {
   SDB_CHECK(p.TN * p.TH * p.TW == BM, "M tile must cover 128 rows");
   SDB_CHECK(p.N % 32 == 0, "N must be a multiple of 32");
-  SDB_CHECK(p.cluster == 1 || (p.cluster == 2 && (p.tiles_n * p.tiles_h * p.tiles_w) % 2 == 0), "cluster pairing needs an even M-tile count");
+  SDB_CHECK(p.cluster == 1 || (p.cluster == 2 && (p.tiles_n * p.tiles_h * p.tiles_w) % 2 == 0 && p.split_k == 1), "CTA pairs need an even M-tile count and no split-K");
 #define SDB_DISPATCH(bn)                                             \
   case bn:                                                           \
     if (passes == 1) launch_bn<bn, 1>(maps, p, stream);              \

@@ -246,10 +246,9 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.tiles_n = (a0.n + p.TN - 1) / p.TN;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
 
-  // Optional CTA pairs along M sharing each weight tile by TMA multicast ("cluster" option, default off: measured
-  // neutral on B200 — operand delivery is bounded per SM, not by L2 reads — and it forbids 2 CTAs/SM; see
-  // profiles/r1_gemm_layers.md). Needs an even number of M tiles.
-  const bool pair = c.opt_cluster && (m_tiles % 2 == 0);
+  // CTA pairs along M issue one cta_group::2 MMA (256 x BN): each CTA stages only half of the weight tile.
+  // Needs an even number of M tiles and no split-K (decided below).
+  bool pair = c.opt_cluster && (m_tiles % 2 == 0);
   // N tile (measured per layer in profiles/r1_gemm_layers.md): 160 divides the UNet widths 320/640/1280 evenly
   int BN;
   if (ep.geglu)
@@ -263,7 +262,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   else
     BN = 64;
   const int n_tiles = (w.N + BN - 1) / BN;
-  p.cluster = pair ? 2 : 1;
+
 
   // split-K when the grid cannot fill the machine and the K loop is long
   const int iters = p.num_taps * p.kc;
@@ -276,6 +275,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       if (split < 1) split = 1;
     }
   }
+  if (split > 1) pair = false;
+  p.cluster = pair ? 2 : 1;
   if (split > 1) {  // no empty K ranges: every split must own at least one iteration
     const int per = (iters + split - 1) / split;
     split = (iters + per - 1) / per;
