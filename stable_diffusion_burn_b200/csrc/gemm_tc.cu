@@ -490,7 +490,7 @@ static void launch_bn(const GemmMaps& maps, const GemmParams& p, cudaStream_t st
 void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream) {
   SDB_CHECK(p.TN * p.TH * p.TW == BM, "M tile must cover 128 rows");
   SDB_CHECK(p.N % 32 == 0, "N must be a multiple of 32");
-  SDB_CHECK(p.cluster == 1 || (p.cluster == 2 && (p.tiles_n * p.tiles_h * p.tiles_w) % 2 == 0 && p.split_k == 1), "CTA pairs need an even M-tile count and no split-K");
+  SDB_CHECK(p.cluster == 1 || (p.cluster == 2 && (p.tiles_n * p.tiles_h * p.tiles_w) % 2 == 0), "CTA pairs need an even M-tile count");
 #define SDB_DISPATCH(bn)                                             \
   case bn:                                                           \
     if (passes == 1) launch_bn<bn, 1>(maps, p, stream);              \

@@ -253,6 +253,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   int BN;
   if (ep.geglu)
     BN = 128;
+  else if (pair && c.opt_pair_bn256 && w.N % 256 == 0 && (long long)m_tiles * (w.N / 256) >= 64)
+    BN = 256;  // pair tile 256 x 256: the fewest operand bytes per FLOP
   else if (w.N % 160 == 0)
     BN = 160;
   else if (w.N % 256 == 0 && (long long)m_tiles * (w.N / 256) >= 296)
@@ -269,14 +271,14 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   int split = 1;
   if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
     const int ctas = m_tiles * n_tiles;
-    if (ctas <= 74 && iters >= 16) {
-      // floor: ctas*split must stay within ONE wave of the 148 SMs (a 2-wave grid costs 2x, see profiles/r1)
-      split = std::min(std::min(148 / ctas, iters / 8), 16);
+    if (ctas <= 74 && iters >= 32) {
+      // floor: ctas*split must stay within ONE wave of the 148 SMs (a 2-wave grid costs 2x, see profiles/r1);
+      // every split keeps >= 16 k-chunks so the rendezvous + fold stays small against its mainloop
+      split = std::min(std::min(148 / ctas, iters / 16), 16);
       if (split < 1) split = 1;
     }
   }
-  if (split > 1) pair = false;
-  p.cluster = pair ? 2 : 1;
+  p.cluster = pair ? 2 : 1;  // pairs and split-K compose: a cluster spans x only, both CTAs share blockIdx.z
   if (split > 1) {  // no empty K ranges: every split must own at least one iteration
     const int per = (iters + split - 1) / split;
     split = (iters + per - 1) / per;

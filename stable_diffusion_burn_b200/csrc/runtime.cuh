@@ -91,7 +91,8 @@ struct Ctx {
   int opt_precision = 0;  // 0 = per-layer policy, 1/2/3 = force
   int opt_graphs = 1;
   int opt_splitk = 1;
-  int opt_cluster = 0;    // CTA-pair TMA multicast of weight tiles (measured neutral; kept as an option)
+  int opt_pair_bn256 = 0;
+  int opt_cluster = 1;    // CTA pairs issue cta_group::2 MMAs (256 x BN) wherever the M-tile count is even and K is not split
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> prof;
