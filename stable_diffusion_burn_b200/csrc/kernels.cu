@@ -262,12 +262,21 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
   if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1u) == (unsigned)(chunks - 1);
   __syncthreads();
   if (s_last) {
-    if (threadIdx.x < 64) {
-      __threadfence();
+    // fold the per-CTA partials: 4 threads per statistic, each a contiguous quarter of the chunks (fixed order)
+    __shared__ double s_fold[4][64];
+    __threadfence();
+    {
+      const int stat = threadIdx.x & 63, part = threadIdx.x >> 6;
+      const int per = (chunks + 3) / 4;
+      const int c0 = part * per, c1 = min(chunks, c0 + per);
       double acc = 0.0;
-      for (int ch = 0; ch < chunks; ++ch) acc += (double)__ldcg(&partials[((size_t)n * chunks + ch) * 64 + threadIdx.x]);
-      sums[(size_t)n * 64 + threadIdx.x] = acc;  // [n][32][2]
+#pragma unroll 4
+      for (int ch = c0; ch < c1; ++ch) acc += (double)__ldcg(&partials[((size_t)n * chunks + ch) * 64 + stat]);
+      s_fold[part][stat] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x < 64)
+      sums[(size_t)n * 64 + threadIdx.x] = ((s_fold[0][threadIdx.x] + s_fold[1][threadIdx.x]) + s_fold[2][threadIdx.x]) + s_fold[3][threadIdx.x];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(&flags[n], 1u);
@@ -321,7 +330,7 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
 }
 
 static int gn_fused_pix(int n, int HW) {
-  int pix = (int)((((long long)HW * n) + 591) / 592);
+  int pix = (int)((((long long)HW * n) + 295) / 296);  // <= 296 CTAs (2 per SM): short fold, always co-resident
   return pix < 8 ? 8 : pix;
 }
 size_t gn_fused_partial_floats(int n, int HW) { return (size_t)n * ceil_div(HW, gn_fused_pix(n, HW)) * 64; }
