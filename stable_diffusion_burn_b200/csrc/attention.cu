@@ -158,6 +158,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     for (int j = 0; j < T; ++j) {
       const int st = j % ST;
       for (int g = 0; g < NG; ++g) {
+        // S_g(j+1) first: it only needs the group to have copied S_g(j) out of TMEM, so it runs while the group is
+        // still in its exponentials and the next softmax never waits for the tensor pipe
+        if (j + 1 < T) issue_qk(g, j + 1);
         if (g == 0) mbar_wait(&v_full[st], (j / ST) & 1);
         mbar_wait(&p_full[g], j & 1);
         tc_fence_after();
@@ -174,7 +177,6 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           umma_commit(&pv_done[g]);
         }
         __syncwarp();
-        if (j + 1 < T) issue_qk(g, j + 1);
       }
     }
   } else {
@@ -198,15 +200,19 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&s_free[g]);
       const int valid = min(128, kvlen - j * 128);
-      float mx = -INFINITY;
+      // 8 independent max chains (a single chain of 128 dependent FMNMX would cost ~500 cycles of pure latency)
+      float mxa[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) mxa[a] = -INFINITY;
       if (valid == 128) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sv[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+          if (i < valid) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sv[i]));
       }
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float m_new = fmaxf(m_run, mx * sl2);
       const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
       if (j > 0) {
@@ -225,7 +231,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           tmem_st_wait();
         }
       }
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums (ILP), folded in fixed order below
       const uint32_t prow_s = smem_u32(prow);
       auto emit = [&](auto masked) {
 #pragma unroll
@@ -240,7 +246,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
               p0 = (i0 < valid) ? p0 : 0.f;
               p1 = (i0 + 1 < valid) ? p1 : 0.f;
             }
-            sum += p0 + p1;  // fp32 terms; the fp16 rounding of P is unbiased and averages out over the row
+            sum4[e] += p0 + p1;  // fp32 terms; the fp16 rounding of P is unbiased and averages out over the row
             const __half2 hp = __floats2half2_rn(p0, p1);
             w[e] = *reinterpret_cast<const uint32_t*>(&hp);
           }
@@ -254,6 +260,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         emit(std::false_type{});
       else
         emit(std::true_type{});
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l_run = l_run * alpha + sum;
       m_run = m_new;
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
