@@ -66,18 +66,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -143,16 +131,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// multicast variants: the box lands at the same smem offset of every CTA in `mask`, and each of those CTAs'
-// mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
 // 2-SM (cta_group::2) loads: data lands in the issuing CTA's smem, the transaction bytes are reported to an
 // mbarrier that may live in the peer CTA of the pair (shared::cluster address, see mapa_shared)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -242,31 +220,10 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// A operand from TMEM (used by attention: P stays in tensor memory)
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// same, arriving on the barrier at this smem offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
 }
 
 // Instruction descriptor for kind::f16: fp16 (or bf16) A/B K-major, fp32 accumulate.
@@ -289,19 +246,6 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;            // SWIZZLE_128B
   return d;
 }
-// MN-major operand (e.g. V as the B operand of P.V with V stored [keys][d]): 64 MN elements
-// (128 B) contiguous per K row, 128B swizzle; LBO = byte distance between 64-wide MN blocks,
-// SBO = byte distance between 8-row K groups.
-__device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
-  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
-
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (one row per thread).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

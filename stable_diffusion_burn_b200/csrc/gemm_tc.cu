@@ -4,10 +4,10 @@
 // (call sites: src/model/unet/mod.rs:716,726,729 ResBlock convs; :468,479 proj_in/out;
 //  :645-651 q/k/v/out; :580,553 GEGLU/ff; src/model/autoencoder/mod.rs:513-528, 567-606).
 //
-// One CTA = one 128 x BN output tile (x one K split). Warp roles:
+// One CTA = one 128 x BN output tile (x one K split); with CG = 2 a CTA pair shares one 256 x BN MMA. Warp roles:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 5-D activation boxes + 2-D weight boxes)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (fp16 x fp16 -> fp32 in TMEM)
-//   warps 2-5: epilogue (tcgen05.ld -> bias / time-embedding row / residual / GEGLU -> global)
+//   warps 2-9: epilogue (tcgen05.ld -> smem transpose -> bias / time-embedding row / residual / GEGLU -> global)
 // Multi-pass products (PASSES = 2, 3) add the low-order fp16 halves of the operands
 // (A_lo*B_hi, A_hi*B_lo) into the same accumulator for fp32-class accuracy.
 #include "gemm_tc.cuh"
@@ -43,7 +43,6 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  uint32_t* tile_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -380,54 +379,6 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     else
       tmem_dealloc(tmem_base, TMEM_COLS);
   }
-}
-
-// ------------------------------------------------------------------ split-K reduction + epilogue
-__global__ void splitk_reduce_kernel(const GemmParams p, long long Mtot) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of the output
-  const int n4 = p.N / 4;
-  if (idx >= Mtot * n4) return;
-  const long long m = idx / n4;
-  const int col = int(idx - m * n4) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < p.split_k; ++z) {  // fixed order: deterministic
-    float4 v = *reinterpret_cast<const float4*>(p.ws + ((long long)z * Mtot + m) * p.N + col);
-    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-  }
-  if (p.bias) {
-    float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
-  }
-  if (p.rowbias) {
-    const long long pn = m / ((long long)p.OH * p.OW);
-    float4 b = *reinterpret_cast<const float4*>(p.rowbias + pn * p.N + col);
-    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
-  }
-  if (p.residual) {
-    float4 b = *reinterpret_cast<const float4*>(p.residual + m * p.ldc + col);
-    acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
-  }
-  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + m * p.ldc + col) = acc;
-  if (p.out_f16) {
-    __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
-    __half2* o = reinterpret_cast<__half2*>(p.out_f16 + m * p.ldc16 + col);
-    o[0] = h0, o[1] = h1;
-    if (p.out_f16_lo) {
-      float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-      __half2* ol = reinterpret_cast<__half2*>(p.out_f16_lo + m * p.ldc16 + col);
-      ol[0] = __floats2half2_rn(acc.x - f0.x, acc.y - f0.y);
-      ol[1] = __floats2half2_rn(acc.z - f1.x, acc.w - f1.y);
-    }
-  }
-}
-
-void splitk_reduce_launch(const GemmParams& p, cudaStream_t stream) {
-  const long long Mtot = (long long)p.nimg * p.OH * p.OW;
-  const long long work = Mtot * (p.N / 4);
-  const int threads = 256;
-  const long long blocks = (work + threads - 1) / threads;
-  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(p, Mtot);
-  SDB_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------ launcher

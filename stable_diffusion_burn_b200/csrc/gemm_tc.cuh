@@ -10,8 +10,8 @@ namespace sdb {
 // D (fp32, TMEM) [128 rows = TN*TH*TW output pixels][BN output channels].
 struct GemmMaps {
   CUtensorMap a[2][2];  // [source 0/1][hi/lo]
-  CUtensorMap b[2];     // [hi/lo]  box {64, BN}   (cluster = 1)  or  {64, BN/2} (cluster = 2: each CTA of an
-                        //          M-pair fetches half of the shared weight tile and multicasts it to both)
+  CUtensorMap b[2];     // [hi/lo]  box {64, BN} (cluster = 1) or {64, BN/2} (cluster = 2: each CTA of a pair
+                        //          stages the half of the weight tile that the cta_group::2 MMA reads from it)
 };
 
 struct GemmParams {
@@ -24,7 +24,7 @@ struct GemmParams {
   int num_taps;
   int8_t tap_dh[9], tap_dw[9], tap_ph[9];
   int split_k;
-  int cluster;             // 1, or 2 = CTA pairs along M share every weight tile through TMA multicast
+  int cluster;             // 1, or 2 = CTA pairs along M issue tcgen05.mma.cta_group::2 (256 x BN)
   // epilogue
   float* out_f32;          // [M][ldc] or null
   __half* out_f16;         // [M][ldc16] or null (hi part)
@@ -46,7 +46,6 @@ struct GemmLaunch {
 };
 
 void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream);
-void splitk_reduce_launch(const GemmParams& p, cudaStream_t stream);
 int gemm_tc_smem_bytes(int BN, int passes, int stages);
 
 }  // namespace sdb

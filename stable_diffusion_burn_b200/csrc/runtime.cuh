@@ -36,7 +36,7 @@ struct TensorInfo {
 
 enum KernelClass : int {
   KC_GEMM = 0,
-  KC_SPLITK,
+  KC_SPLITK,  // kept for the class table layout: the split-K fold now happens inside gemm_tc
   KC_ATTN,
   KC_GN_STATS,
   KC_PREP,
