@@ -83,6 +83,13 @@ int sdb_sample_image(sdb_ctx* ctx, const float* context, int n, int L, const flo
                      double guidance_scale, int n_steps, const float* init_latent, uint64_t seed,
                      int H, int W, uint8_t* rgb);
 
+/* ---- text encoder (the first "next" row after the hot path) ------------------ */
+/* CLIP::forward (src/model/clip/mod.rs:56-75): token ids [n,L] (L <= 77, NOT padded — the reference does not pad,
+ * src/model/stablediffusion/mod.rs:198-211) -> context [n,L,768]. The ids come from SimpleTokenizer::encode
+ * (src/tokenizer.rs:175-195), mirrored host-side in stable_diffusion_burn_b200/tokenizer.py. */
+int sdb_clip_forward(sdb_ctx* ctx, const int32_t* tokens, int n, int L, float* out);
+int sdb_clip_forward_dev(sdb_ctx* ctx, const int32_t* d_tokens, int n, int L, float* d_out, void* stream);
+
 /* ---- hot path, device buffers (zero-copy callers) ------------------------------------------ */
 int sdb_unet_forward_dev(sdb_ctx* ctx, const float* d_x, int32_t timestep, const float* d_context,
                          int n, int H, int W, int L, float* d_out, void* stream);

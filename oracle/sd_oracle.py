@@ -128,8 +128,13 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def qkv_attention(q, k, v, n_head):
-    """reference src/model/attention.rs:5-45 (== src/backend.rs:88-128), mask=None."""
+def attn_decoder_mask(seq_length, dtype=torch.float32):
+    """reference src/backend.rs:130-139: zeros with -inf strictly above the diagonal."""
+    return torch.full((seq_length, seq_length), float("-inf"), dtype=dtype).triu(1)
+
+
+def qkv_attention(q, k, v, n_head, mask=None):
+    """reference src/model/attention.rs:5-45 (== src/backend.rs:88-128); mask: additive [n_qctx, n_ctx] or None."""
     n_batch, n_qctx, n_state = q.shape
     n_ctx = k.shape[1]
     scale = (n_state / n_head) ** -0.25
@@ -138,6 +143,8 @@ def qkv_attention(q, k, v, n_head):
     k = k.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2).transpose(-1, -2) * scale
     v = v.reshape(n_batch, n_ctx, n_head, n_hstate).transpose(1, 2)
     qk = _q(q, "q") @ _q(k, "q")
+    if mask is not None:
+        qk = qk + mask[:n_qctx, :n_ctx]
     # burn softmax: exp(x - max) / sum
     w = qk - qk.amax(dim=3, keepdim=True)
     w = w.exp()
@@ -265,6 +272,25 @@ def unet_forward(P, x, t, context, taps=None, prefix="unet"):
     x = group_norm(P, f"{prefix}/norm_out", x)
     x = silu(x)
     return conv2d(P, f"{prefix}/conv_out", x, padding=1)
+
+
+# ------------------------------------------------------------------ CLIP text encoder
+def clip_forward(P, tokens, prefix="clip"):
+    """reference src/model/clip/mod.rs:56-75 (+ block :109-115, attention :158-180, MLP/QuickGELU :204-227).
+    tokens: int64 [n, L] -> [n, L, 768]."""
+    from stable_diffusion_burn_b200 import topology as T
+    n, L = tokens.shape
+    mask = attn_decoder_mask(L, P.dtype)
+    x = P(f"{prefix}/token_embedding/weight")[tokens] + P(f"{prefix}/position_embedding/weight")[:L].unsqueeze(0)
+    for i in range(T.CLIP_LAYERS):
+        b = f"{prefix}/blocks/{i}"
+        h = nn_layer_norm(P, f"{b}/attn_ln", x)
+        q, k, v = linear(P, f"{b}/attn/query", h), linear(P, f"{b}/attn/key", h), linear(P, f"{b}/attn/value", h)
+        x = x + linear(P, f"{b}/attn/out", qkv_attention(q, k, v, T.CLIP_HEADS, mask))
+        h = linear(P, f"{b}/mlp/fc1", nn_layer_norm(P, f"{b}/mlp_ln", x))
+        h = h * torch.sigmoid(h * 1.702)  # QuickGELU, clip/mod.rs:224-226
+        x = x + linear(P, f"{b}/mlp/fc2", h)
+    return nn_layer_norm(P, f"{prefix}/layer_norm", x)
 
 
 # ------------------------------------------------------------------ VAE decoder

@@ -38,6 +38,8 @@ SIGNATURES = [
     ("sdb_latent_to_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _u8p]),
     ("sdb_sample_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_double, C.c_int, _f32p,
                                    C.c_uint64, C.c_int, C.c_int, _u8p]),
+    ("sdb_clip_forward", C.c_int, [_ctx, C.POINTER(C.c_int32), C.c_int, C.c_int, _f32p]),
+    ("sdb_clip_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("sdb_unet_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]),
     ("sdb_decode_latent_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -159,6 +161,15 @@ class Context:
         L = context.shape[1]
         out = np.empty_like(x)
         self.check(self.lib.sdb_unet_forward(self.h, ptr(x), int(t), ptr(context), n, H, W, L, ptr(out)))
+        return out
+
+    def clip_forward(self, tokens):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        if t.ndim == 1:
+            t = t[None]
+        n, L = t.shape
+        out = np.empty((n, L, 768), np.float32)
+        self.check(self.lib.sdb_clip_forward(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)), n, L, ptr(out)))
         return out
 
     def decode_latent(self, latent):

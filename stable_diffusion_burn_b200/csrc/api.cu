@@ -213,6 +213,21 @@ int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, con
   API_END
 }
 
+int sdb_clip_forward(sdb_ctx* ctx, const int32_t* tokens, int n, int L, float* out) {
+  API_BEGIN(ctx)
+  need_final(c);
+  SDB_CHECK(tokens && out, "null argument");
+  model_clip_forward_host(c, tokens, n, L, out);
+  API_END
+}
+
+int sdb_clip_forward_dev(sdb_ctx* ctx, const int32_t* d_tokens, int n, int L, float* d_out, void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_clip_forward_dev(c, d_tokens, n, L, d_out, (cudaStream_t)stream);
+  API_END
+}
+
 // ------------------------------------------------------------------------------ options / profiling
 int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
   API_BEGIN(ctx)

@@ -199,7 +199,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[g]);
-      const int valid = min(128, kvlen - j * 128);
+      int valid = min(128, kvlen - j * 128);
+      if (p.causal) valid = max(1, min(valid, q0 + g * 128 + r - j * 128 + 1));  // additive -inf mask above the diagonal
       // 8 independent max chains (a single chain of 128 dependent FMNMX would cost ~500 cycles of pure latency)
       float mxa[8];
 #pragma unroll
@@ -323,6 +324,9 @@ void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtens
   switch (p.dpad) {
     case 48:
       two ? launch_attn<48, 2>(mq, mk, mv, p, st) : launch_attn<48, 1>(mq, mk, mv, p, st);
+      break;
+    case 64:
+      launch_attn<64, 1>(mq, mk, mv, p, st);
       break;
     case 80:
       two ? launch_attn<80, 2>(mq, mk, mv, p, st) : launch_attn<80, 1>(mq, mk, mv, p, st);

@@ -11,6 +11,7 @@ struct AttnParams {
   int k_rows_per_sample;      // row stride between samples in K (= column stride in V^T)
   int q_col0, k_col0;         // first column of head 0 inside the Q / K matrices
   const int* kvlen;           // [nb] valid keys per sample, or null (= Nk)
+  int causal;                 // 1: query row i attends to keys 0..i only
   float scale;                // d^-1/2
   __half* out_hi;             // [nb*Nq][ldo], head h at columns h*d
   __half* out_lo;             // optional residual half

@@ -227,6 +227,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const float4 b = *reinterpret_cast<const float4*>(p.residual + o32);
         f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
       }
+      if (p.act == 1) {
+        f.x = f.x / (1.0f + __expf(-1.702f * f.x)), f.y = f.y / (1.0f + __expf(-1.702f * f.y));
+        f.z = f.z / (1.0f + __expf(-1.702f * f.z)), f.w = f.w / (1.0f + __expf(-1.702f * f.w));
+      }
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o32) = f;
       if (p.out_f16) {
         __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};

@@ -35,6 +35,7 @@ struct GemmParams {
   int ldc;                 // row stride of out_f32 / residual (elements)
   int ldc16;               // row stride of out_f16
   int geglu;               // 1: columns are (x|gate) interleaved per tile, output width N/2
+  int act;                 // 1: QuickGELU x*sigmoid(1.702x) on the result (CLIP MLP, clip/mod.rs:224-226)
   float* ws;               // split-K workspace [split][M][N]
   unsigned int* tickets;   // split-K: one counter per output tile, all zero between launches (self-cleaning)
   // output pixel mapping: out row = ((n*OH + h*os + oa)*OW + w*os + ob)

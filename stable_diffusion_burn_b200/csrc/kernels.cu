@@ -678,6 +678,32 @@ void time_embed_launch(const int* t, const float* w1, const float* b1, const flo
   SDB_CUDA(cudaGetLastError());
 }
 
+// ============================================================ CLIP token + position embedding
+// x[s][l][:] = E[tok[s][l]] + Pos[l] for l < L, zero rows up to Lp (reference clip/mod.rs:62-68)
+__global__ void embed_tokens_kernel(const int* __restrict__ tok, const float* __restrict__ E, const float* __restrict__ Pos,
+                                    int L, int Lp, int D, int vocab, float* __restrict__ x) {
+  pdl_enter();
+  const int row = blockIdx.x;  // s*Lp + l
+  const int s = row / Lp, l = row % Lp;
+  float4* dst = reinterpret_cast<float4*>(x + (size_t)row * D);
+  if (l >= L) {
+    for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int id = tok[s * L + l];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4* e = reinterpret_cast<const float4*>(E + (size_t)id * D);
+  const float4* pp = reinterpret_cast<const float4*>(Pos + (size_t)l * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 a = e[i], b = pp[i];
+    dst[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+void embed_tokens_launch(const int* tok, const float* E, const float* Pos, int n, int L, int Lp, int D, int vocab, float* x,
+                         cudaStream_t st) {
+  launch_k(embed_tokens_kernel, dim3(n * Lp), dim3(192), 0, st, tok, E, Pos, L, Lp, D, vocab, x);
+}
+
 // ============================================================ sampler elementwise
 __global__ void cfg_ddim_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ lat,
                                 long long count, float scale, float sqrt_1m_at, float sqrt_at, float sqrt_aprev,

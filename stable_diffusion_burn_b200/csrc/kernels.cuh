@@ -64,6 +64,10 @@ void time_embed_launch(const int* t_dev, const float* w1, const float* b1, const
 // y[N] = x[K] @ W[K][N] + b  (tiny GEMV, W fp32 [in,out])
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st);
 
+// ---- CLIP embedding lookup: x [n][Lp][D] = E[tok] + Pos, rows l >= L zero (reference clip/mod.rs:62-68)
+void embed_tokens_launch(const int* tok, const float* E, const float* Pos, int n, int L, int Lp, int D, int vocab, float* x,
+                         cudaStream_t st);
+
 // ---- sampler elementwise (reference stablediffusion/mod.rs:152-156, 190-191)
 // pred = u + (c-u)*scale ; x0 = (lat - pred*sqrt(1-a_t))/sqrt(a_t) ; lat' = x0*sqrt(a_prev) + pred*sqrt(1-a_prev)
 // latent holds 2*count floats: the update is written to both halves (uncond | cond inputs of the next step)

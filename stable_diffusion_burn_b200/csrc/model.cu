@@ -172,6 +172,21 @@ void model_finalize(Ctx& c) {
     if (m.dec[i].has_up) pack_conv(c, m.dec[i].up, /*up2=*/true), m.dec[i].up.passes = g_vae_passes_up;
   }
   pack_norm(c, m.vae_norm_out);
+  // ---- CLIP text encoder
+  for (ClipBlockW& cb : m.clip.blocks) {
+    pack_norm(c, cb.attn_ln), pack_norm(c, cb.mlp_ln);
+    cb.w_qk.p = alloc_half2(c.packed, (size_t)2 * 768 * 768), cb.w_qk.N = 1536, cb.w_qk.K = 768;
+    pack_linear_launch(mptr(c, cb.query.wi), 768, 768, cb.w_qk.p, 0, c.stream);
+    pack_linear_launch(mptr(c, cb.key.wi), 768, 768, cb.w_qk.p, 768, c.stream);
+    cb.bias_qk = c.packed.get<float>(1536);
+    SDB_CUDA(cudaMemcpyAsync(cb.bias_qk, mptr(c, cb.query.bi), 768 * 4, cudaMemcpyDeviceToDevice, c.stream));
+    SDB_CUDA(cudaMemcpyAsync(cb.bias_qk + 768, mptr(c, cb.key.bi), 768 * 4, cudaMemcpyDeviceToDevice, c.stream));
+    pack_lin(c, cb.value), pack_lin(c, cb.out), pack_lin(c, cb.fc1), pack_lin(c, cb.fc2);
+    // softmax rows sum to one, so P.(V + 1 b_v^T) = P.V + b_v^T: fold the value bias into the out-projection bias
+    cb.bias_out = c.packed.get<float>(768);
+    gemv_launch(mptr(c, cb.value.bi), mptr(c, cb.out.wi), mptr(c, cb.out.bi), 768, 768, cb.bias_out, c.stream);
+  }
+  pack_norm(c, m.clip.ln_final);
   // ---- schedule
   m.alphas_host.resize(1000);
   SDB_CUDA(cudaMemcpyAsync(m.alphas_host.data(), mptr(c, m.alphas_i), 4000, cudaMemcpyDeviceToHost, c.stream));
@@ -966,6 +981,97 @@ void model_sample_host(Ctx& c, const float* context, int n, int L, const float* 
     throw;
   }
   free_all();
+}
+
+// ================================================================================ CLIP text encoder
+// reference src/model/clip/mod.rs:56-75 (CLIP::forward), :109-115 (block), :158-180 (attention with the causal mask of
+// src/backend.rs:130-139), :204-227 (MLP with QuickGELU). tokens [n][L] int32 -> out [n][L][768]. SURVEY §8f row f1.
+void model_clip_forward_dev(Ctx& c, const int* d_tok, int n, int L, float* d_out, cudaStream_t caller) {
+  Model& m = M(c);
+  SDB_CHECK(n >= 1 && L >= 1 && L <= 77, "clip_forward: 1 <= L <= 77 (position table), n >= 1");
+  StreamJoin join(c, caller);
+  c.work.reset();
+  Fwd f(c, n);
+  const int D = 768, heads = 12;
+  const int Lp = round_up(L, 8);           // per-sample row pitch: keeps every TMA tile origin 16-byte aligned
+  const int Mr = n * Lp, Mp = round_up(Mr, 32);
+  float* x = c.work.get<float>((size_t)Mr * D);
+  float* y = c.work.get<float>((size_t)Mr * D);
+  Half2Ptr l16 = f.half2((size_t)Mr * D, true), o16 = f.half2((size_t)Mr * D, true), h16 = f.half2((size_t)Mr * 4 * D, true);
+  __half* qk = c.work.get<__half>((size_t)Mr * 2 * D);
+  __half* vT = c.work.get<__half>((size_t)D * Mp);
+  // pad rows (l >= L) never reach a real row (causal mask, row-wise ops) but must stay finite: 0 * NaN would poison P.V
+  SDB_CUDA(cudaMemsetAsync(o16.hi, 0, (size_t)Mr * D * 2, c.stream));
+  SDB_CUDA(cudaMemsetAsync(o16.lo, 0, (size_t)Mr * D * 2, c.stream));
+  {
+    KernelScope ks(c, KC_ELEMENTWISE);
+    embed_tokens_launch(d_tok, mptr(c, m.clip.tok_i), mptr(c, m.clip.pos_i), n, L, Lp, D, 49408, x, c.stream);
+  }
+  auto ln = [&](const NormW& nw, Half2Ptr o, float* o32) {
+    KernelScope ks(c, KC_LAYERNORM);
+    layernorm_launch(x, Mr, D, nw.gamma, nw.beta, 1e-5f, o, o32, c.stream);
+  };
+  for (ClipBlockW& cb : m.clip.blocks) {
+    ln(cb.attn_ln, l16, nullptr);
+    {
+      Epilogue ep;
+      ep.out_f16.hi = qk, ep.bias = cb.bias_qk;
+      run_gemm(c, G_LINEAR, f.rows_operand(l16, Mr, D), nullptr, cb.w_qk, 3, ep);
+    }
+    {
+      WeightOp tok;
+      tok.p = l16, tok.N = Mp, tok.rows = Mr, tok.K = D;
+      Epilogue ep;
+      ep.out_f16.hi = vT;
+      run_gemm(c, G_LINEAR, f.rows_operand(cb.value.packed.p, D, D), nullptr, tok, 3, ep);
+    }
+    {
+      AttnOp at;
+      at.q = qk, at.ldq = 2 * D, at.q_col0 = 0, at.q_rows = Lp;
+      at.k = qk, at.ldk = 2 * D, at.k_col0 = D, at.k_rows = Lp;
+      at.vT = vT, at.ldv = Mp;
+      at.nb = n, at.heads = heads, at.d = 64, at.dpad = 64, at.Nq = L, at.Nk = L;
+      at.causal = 1;
+      at.out = o16, at.ldo = D;
+      run_attention(c, at);
+    }
+    {
+      Epilogue ep;
+      ep.out_f32 = x, ep.residual = x, ep.bias = cb.bias_out;
+      run_gemm(c, G_LINEAR, f.rows_operand(o16, Mr, D), nullptr, cb.out.packed, 3, ep);
+    }
+    ln(cb.mlp_ln, l16, nullptr);
+    {
+      Epilogue ep;
+      ep.out_f16 = h16, ep.bias = cb.fc1.bias, ep.act = 1;
+      run_gemm(c, G_LINEAR, f.rows_operand(l16, Mr, D), nullptr, cb.fc1.packed, 3, ep);
+    }
+    {
+      Epilogue ep;
+      ep.out_f32 = x, ep.residual = x, ep.bias = cb.fc2.bias;
+      run_gemm(c, G_LINEAR, f.rows_operand(h16, Mr, 4 * D), nullptr, cb.fc2.packed, 3, ep);
+    }
+  }
+  ln(m.clip.ln_final, Half2Ptr{}, y);
+  SDB_CUDA(cudaMemcpy2DAsync(d_out, (size_t)L * D * 4, y, (size_t)Lp * D * 4, (size_t)L * D * 4, n, cudaMemcpyDeviceToDevice,
+                             c.stream));
+}
+
+void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out) {
+  int* d_t = nullptr;
+  float* d_o = nullptr;
+  try {
+    SDB_CUDA(cudaMalloc(&d_t, (size_t)n * L * 4));
+    SDB_CUDA(cudaMalloc(&d_o, (size_t)n * L * 768 * 4));
+    SDB_CUDA(cudaMemcpyAsync(d_t, tokens, (size_t)n * L * 4, cudaMemcpyHostToDevice, c.stream));
+    model_clip_forward_dev(c, d_t, n, L, d_o, c.stream);
+    SDB_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * L * 768 * 4, cudaMemcpyDeviceToHost, c.stream));
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+  } catch (...) {
+    cudaFree(d_t), cudaFree(d_o);
+    throw;
+  }
+  cudaFree(d_t), cudaFree(d_o);
 }
 
 // ================================================================================ attention unit-test entry

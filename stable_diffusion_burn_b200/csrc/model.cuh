@@ -21,6 +21,8 @@ void model_sample_host(Ctx& c, const float* context, int n, int L, const float* 
 void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float* d_uncond, int Lu, double scale,
                       int n_steps, const float* d_init_latent, int H, int W, float* d_latent_out, uint8_t* d_rgb,
                       cudaStream_t caller);
+void model_clip_forward_dev(Ctx& c, const int* d_tokens, int n, int L, float* d_out, cudaStream_t caller);
+void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out);
 void model_test_attention(Ctx& c, const float* q, const float* k, const float* v, int n, int Nq, int Nk, int C, int heads,
                           float* out);
 

@@ -7,7 +7,7 @@
 
 namespace sdb {
 
-enum { K_CONV_W = 0, K_CONV_B, K_LIN_W, K_LIN_B, K_NORM_G, K_NORM_B, K_SCHED };
+enum { K_CONV_W = 0, K_CONV_B, K_LIN_W, K_LIN_B, K_NORM_G, K_NORM_B, K_SCHED, K_EMB };
 
 // ------------------------------------------------------------------ registry builder
 struct Builder {
@@ -178,6 +178,23 @@ void model_create(Ctx& c) {
   }
   b.norm(m->vae_norm_out, d + "/norm_out", 128);
   b.conv(m->vae_conv_out, d + "/conv_out", 128, 3, 3);
+  // ---- CLIP text encoder (clip/mod.rs:25-44, CLIPConfig::new(49408,768,12,77,12))
+  m->clip.tok_i = b.add("clip/token_embedding/weight", {49408, 768}, K_EMB, 768);
+  m->clip.pos_i = b.add("clip/position_embedding/weight", {77, 768}, K_EMB, 768);
+  m->clip.blocks.resize(12);
+  for (int i = 0; i < 12; ++i) {
+    ClipBlockW& cb = m->clip.blocks[i];
+    const std::string bn = "clip/blocks/" + std::to_string(i);
+    b.norm(cb.attn_ln, bn + "/attn_ln", 768);
+    b.lin(cb.query, bn + "/attn/query", 768, 768);
+    b.lin(cb.key, bn + "/attn/key", 768, 768);
+    b.lin(cb.value, bn + "/attn/value", 768, 768);
+    b.lin(cb.out, bn + "/attn/out", 768, 768);
+    b.norm(cb.mlp_ln, bn + "/mlp_ln", 768);
+    b.lin(cb.fc1, bn + "/mlp/fc1", 768, 3072);
+    b.lin(cb.fc2, bn + "/mlp/fc2", 3072, 768);
+  }
+  b.norm(m->clip.ln_final, "clip/layer_norm", 768);
   // ---- sampler schedule (stablediffusion/mod.rs:44)
   m->alphas_i = b.add("alpha_cumulative_products", {1000}, K_SCHED, 1);
 
@@ -196,7 +213,7 @@ void model_create(Ctx& c) {
 
   c.master.init((b.off + 64) * sizeof(float));
   c.master.off = b.off * sizeof(float);
-  c.packed.init(env_gb("SDB_PACKED_GB", 5.5));
+  c.packed.init(env_gb("SDB_PACKED_GB", 6.5));
   c.work.init(env_gb("SDB_WORK_GB", 24.0));
   SDB_CUDA(cudaMalloc(&c.splitk_tickets, 65536 * sizeof(unsigned int)));
   SDB_CUDA(cudaMemsetAsync(c.splitk_tickets, 0, 65536 * sizeof(unsigned int), c.stream));
@@ -251,6 +268,9 @@ void model_init_synthetic(Ctx& c, uint32_t seed) {
         break;
       case K_NORM_B:
         bound = 0.1f;
+        break;
+      case K_EMB:
+        bound = (float)std::sqrt(3.0);
         break;
     }
     const uint32_t key = mix32_host(fnv1a32(t.name) + seed);

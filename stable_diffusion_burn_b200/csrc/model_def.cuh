@@ -83,7 +83,21 @@ struct DecoderBlockW {
   ConvW up;
 };
 
+struct ClipBlockW {  // src/model/clip/mod.rs:77-115
+  NormW attn_ln, mlp_ln;
+  LinW query, key, value, out, fc1, fc2;
+  WeightOp w_qk;             // [2*768][768] fused q|k
+  float* bias_qk = nullptr;  // [1536]
+  float* bias_out = nullptr; // out.bias + value.bias @ W_out  (the v bias commutes with the softmax average)
+};
+struct ClipW {
+  int tok_i = -1, pos_i = -1;
+  std::vector<ClipBlockW> blocks;
+  NormW ln_final;
+};
+
 struct Model {
+  ClipW clip;
   // UNet
   LinW lin1_time, lin2_time;
   std::vector<UNetBlockW> in_blocks, out_blocks;

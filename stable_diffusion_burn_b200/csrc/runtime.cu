@@ -158,6 +158,7 @@ void run_attention(Ctx& c, const AttnOp& a) {
   p.q_rows_per_sample = a.q_rows, p.k_rows_per_sample = a.k_rows;
   p.q_col0 = a.q_col0, p.k_col0 = a.k_col0;
   p.kvlen = a.kvlen;
+  p.causal = a.causal;
   p.scale = (float)(1.0 / std::sqrt((double)a.d));
   p.out_hi = a.out.hi, p.out_lo = a.out.lo, p.ldo = a.ldo;
   const CUtensorMap mq = make_mat_map(a.q, a.ldq, (long long)a.nb * a.q_rows, 128);
@@ -298,6 +299,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.rowbias = ep.rowbias;
   p.residual = ep.residual;
   p.geglu = ep.geglu;
+  p.act = ep.act;
   const int nout = ep.geglu ? w.N / 2 : w.N;
   p.ldc = ep.ldc ? ep.ldc : nout;
   p.ldc16 = ep.ldc16 ? ep.ldc16 : nout;

@@ -74,6 +74,7 @@ struct Epilogue {
   const float* rowbias = nullptr;
   const float* residual = nullptr;
   int geglu = 0;
+  int act = 0;    // 1 = QuickGELU
   int ldc = 0;    // 0 -> N (or N/2 for geglu)
   int ldc16 = 0;  // 0 -> N (or N/2 for geglu)
 };
@@ -138,6 +139,7 @@ struct AttnOp {
   int ldv = 0;
   int nb = 1, heads = 8, d = 0, dpad = 0, Nq = 0, Nk = 0;
   const int* kvlen = nullptr;
+  int causal = 0;  // 1: key j visible to query i only if j <= i (CLIP, src/backend.rs:130-139)
   Half2Ptr out;
   int ldo = 0;
 };

@@ -39,13 +39,33 @@ class Autoencoder:
         return self._c.decode_latent(latent)
 
 
+class CLIP:
+    def __init__(self, ctx: Context):
+        self._c = ctx
+
+    def forward(self, tokens) -> np.ndarray:
+        """CLIP::forward (src/model/clip/mod.rs:56-75): int ids [n,L] (L <= 77, unpadded) -> [n,L,768]."""
+        return self._c.clip_forward(tokens)
+
+
 class StableDiffusion:
-    """Owns the device context; `diffusion` and `autoencoder` mirror the reference's fields."""
+    """Owns the device context; `diffusion`, `autoencoder` and `clip` mirror the reference's fields."""
 
     def __init__(self, device: int = 0):
         self.ctx = Context(device)
         self.diffusion = UNet(self.ctx)
         self.autoencoder = Autoencoder(self.ctx)
+        self.clip = CLIP(self.ctx)
+
+    # ---- prompt -> context (reference stablediffusion/mod.rs:194-211)
+    def context(self, tokenizer, text: str) -> np.ndarray:
+        """[1, L, 768]: CLIP of "<|startoftext|>{text}<|endoftext|>" (no padding to 77, like the reference)."""
+        ids = tokenizer.encode(f"<|startoftext|>{text}<|endoftext|>")
+        return self.clip.forward(np.asarray(ids, np.int32)[None])
+
+    def unconditional_context(self, tokenizer) -> np.ndarray:
+        """[Lu, 768] = context("").squeeze(0); Lu = 2 for the empty prompt."""
+        return self.context(tokenizer, "")[0]
 
     # ---- weights (reference: load_stable_diffusion / load_record)
     def init_synthetic(self, seed: int = 0):

@@ -13,6 +13,7 @@ bound/offset per kind (fan_in = Cin*k*k for conv, in-features for Linear):
   conv_b, lin_b : bound = 1/sqrt(fan_in), offset 0
   norm_g        : bound = 0.1, offset 1
   norm_b        : bound = 0.1, offset 0
+  emb           : bound = sqrt(3), offset 0     (token / position embeddings)
 """
 from __future__ import annotations
 
@@ -74,6 +75,8 @@ def kind_bound_offset(kind: str, fan_in: int):
         return np.float32(0.1), np.float32(1.0)
     if kind == "norm_b":
         return np.float32(0.1), np.float32(0.0)
+    if kind == "emb":  # unit variance, like burn's N(0,1) embedding initialiser
+        return np.float32(math.sqrt(3.0)), np.float32(0.0)
     raise ValueError(kind)
 
 

@@ -8,7 +8,7 @@ Shapes come from the topology in src/model/unet/mod.rs:35-93 and
 src/model/autoencoder/mod.rs:29-45,153-192.
 
 Each entry: (name, shape, kind, fan_in) with kind in
-  {"conv_w","conv_b","lin_w","lin_b","norm_g","norm_b"}.
+  {"conv_w","conv_b","lin_w","lin_b","norm_g","norm_b","emb"}.
 The C++ library builds the same list independently (csrc/model.cu); a test
 cross-checks the two through sdb_tensor_count / sdb_tensor_info.
 """
@@ -161,8 +161,28 @@ def vae_decoder_params(prefix="autoencoder"):
     return out
 
 
+CLIP_VOCAB, CLIP_STATE, CLIP_HEADS, CLIP_CTX, CLIP_LAYERS = 49408, 768, 12, 77, 12  # stablediffusion/mod.rs:29
+
+
+def clip_params(prefix="clip"):
+    """CLIP text transformer: src/model/clip/mod.rs:25-44, names from src/model/clip/load.rs:15-81."""
+    out = []
+    out.append((f"{prefix}/token_embedding/weight", (CLIP_VOCAB, CLIP_STATE), "emb", CLIP_STATE))
+    out.append((f"{prefix}/position_embedding/weight", (CLIP_CTX, CLIP_STATE), "emb", CLIP_STATE))
+    for i in range(CLIP_LAYERS):
+        b = f"{prefix}/blocks/{i}"
+        _norm(out, f"{b}/attn_ln", CLIP_STATE)
+        for n in ("query", "key", "value", "out"):
+            _lin(out, f"{b}/attn/{n}", CLIP_STATE, CLIP_STATE)
+        _norm(out, f"{b}/mlp_ln", CLIP_STATE)
+        _lin(out, f"{b}/mlp/fc1", CLIP_STATE, 4 * CLIP_STATE)
+        _lin(out, f"{b}/mlp/fc2", 4 * CLIP_STATE, CLIP_STATE)
+    _norm(out, f"{prefix}/layer_norm", CLIP_STATE)
+    return out
+
+
 def all_params():
-    return unet_params() + vae_decoder_params()
+    return unet_params() + vae_decoder_params() + clip_params()
 
 
 if __name__ == "__main__":

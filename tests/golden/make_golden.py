@@ -20,9 +20,39 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 ONLY = set(sys.argv[1:])  # e.g. `make_golden.py batch2_32` regenerates only that UNet case (+ the 2-step sample)
 
 
+CLIP_PROMPT = [49406, 550, 5810, 617, 8661, 2441, 13, 27, 347, 40786, 4160, 91, 285, 49407]  # arbitrary in-vocab ids, sot..eot
+
+
+def clip_tokens():
+    """Token batches of the CLIP fixture: a README-length prompt, the empty prompt, a full 77-id window, a ragged pair."""
+    g = np.random.Generator(np.random.Philox(4242))
+    full = np.concatenate([[49406], g.integers(0, 49406, 75), [49407]]).astype(np.int32)
+    pair = np.stack([np.concatenate([[49406], g.integers(0, 49406, 9), [49407]]),
+                     np.concatenate([[49406], g.integers(0, 49406, 4), [49407] * 6])]).astype(np.int32)
+    return {"prompt": np.asarray(CLIP_PROMPT, np.int32)[None], "empty": np.asarray([[49406, 49407]], np.int32),
+            "full77": full[None], "pair11": pair}
+
+
+def clip_golden():
+    from stable_diffusion_burn_b200 import topology
+    P = O.Params(synth.make_params(0, which=topology.clip_params()))
+    keep = {}
+    with torch.no_grad():
+        for name, tok in clip_tokens().items():
+            y = O.clip_forward(P, torch.from_numpy(tok).long())
+            keep["tok:" + name] = tok
+            keep["out:" + name] = y.numpy()
+            print("clip", name, tuple(y.shape), "rms", float(y.pow(2).mean().sqrt()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "clip.npz"), **keep)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
+    if not ONLY or "clip" in ONLY:
+        clip_golden()
+        if ONLY == {"clip"}:
+            return
     P = O.Params(synth.make_params(0))
     print("params", time.time() - t0, flush=True)
     with torch.no_grad():
