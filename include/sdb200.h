@@ -88,6 +88,7 @@ int sdb_sample_image(sdb_ctx* ctx, const float* context, int n, int L, const flo
  * src/model/stablediffusion/mod.rs:198-211) -> context [n,L,768]. The ids come from SimpleTokenizer::encode
  * (src/tokenizer.rs:175-195), mirrored host-side in stable_diffusion_burn_b200/tokenizer.py. */
 int sdb_clip_forward(sdb_ctx* ctx, const int32_t* tokens, int n, int L, float* out);
+/* device-pointer variant: ids outside [0,49408) are clamped (the host variant rejects them). */
 int sdb_clip_forward_dev(sdb_ctx* ctx, const int32_t* d_tokens, int n, int L, float* d_out, void* stream);
 
 /* ---- hot path, device buffers (zero-copy callers) ------------------------------------------ */

@@ -1058,6 +1058,11 @@ void model_clip_forward_dev(Ctx& c, const int* d_tok, int n, int L, float* d_out
 }
 
 void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out) {
+  SDB_CHECK(n >= 1 && L >= 1 && L <= 77, "clip_forward: 1 <= L <= 77 (position table), n >= 1");
+  // the reference's embedding lookup panics on an id outside the table; the host entry rejects it (the *_dev entry,
+  // which cannot see the ids without a sync, clamps instead)
+  for (long long i = 0; i < (long long)n * L; ++i)
+    SDB_CHECK(tokens[i] >= 0 && tokens[i] < 49408, "clip_forward: token id outside the 49408-entry vocabulary");
   int* d_t = nullptr;
   float* d_o = nullptr;
   try {
