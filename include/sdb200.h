@@ -51,6 +51,16 @@ int sdb_tensor_info(sdb_ctx* ctx, int index, const char** name, int64_t dims[4],
 int sdb_set_tensor(sdb_ctx* ctx, const char* name, const float* host, const int64_t* dims, int ndim);
 /* Reads back the fp32 master copy (tests / checkpoint round trips). */
 int sdb_get_tensor(sdb_ctx* ctx, const char* name, float* host, int64_t count);
+/* load_stable_diffusion (src/model/stablediffusion/load.rs:16-33) for the part of the model on this path: reads every
+ * registry tensor from the reference's dump-dir tree (1-D f32 .npy = [dims..., values...], python/save.py:10-15 <->
+ * src/model/load.rs:17-47; <path>/<tensor name>.npy, the schedule from <path>/alphas_cumprod.npy). Optional files follow
+ * the reference (missing Linear/Conv bias = none, missing GroupNorm weight/bias = ones/zeros); the configuration scalars
+ * the reference reads (eps, n_group, stride, padding, n_head, n_layer, n_steps ...) are validated against the compiled
+ * SD-v1.4 topology and each norm's eps is honoured. Encoder / quant_conv files are not read (not on the path). */
+int sdb_load_dump_dir(sdb_ctx* ctx, const char* path);
+/* load_tensor::<B, D> (src/model/load.rs:30-47) for one file, no context needed: splits the leading `ndim` shape values
+ * from the data. Returns the element count (data may be NULL to probe), or -1 (text via sdb_last_error(NULL)). */
+int64_t sdb_read_dump_tensor(const char* file, int ndim, int64_t* dims, float* data, int64_t capacity);
 /* Fills every tensor with the deterministic synthetic stream documented in
  * stable_diffusion_burn_b200/synth.py (bit-identical to the numpy generator). */
 int sdb_init_synthetic(sdb_ctx* ctx, uint32_t seed);

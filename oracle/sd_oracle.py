@@ -68,8 +68,9 @@ def _q(x, role="a"):
 class Params:
     """name -> tensor, names = reference dump-dir paths (src/model/*/load.rs)."""
 
-    def __init__(self, arrays: dict, dtype=torch.float32):
+    def __init__(self, arrays: dict, dtype=torch.float32, norm_eps=None):
         self.dtype = dtype
+        self.norm_eps = dict(norm_eps or {})  # norm dir -> eps read from a dump-dir (load_group_norm / load_layer_norm)
         self.t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in arrays.items()}
 
     def __call__(self, name):
@@ -110,7 +111,7 @@ def group_norm(P, name, x, n_group=32, eps=1e-5):
     shape = x.shape
     n = shape[0]
     c = shape[1]
-    y = layernorm_noaffine(x.reshape(n, n_group, -1), eps).reshape(shape)
+    y = layernorm_noaffine(x.reshape(n, n_group, -1), P.norm_eps.get(name, eps)).reshape(shape)
     aff = [1] * x.dim()
     aff[1] = c
     return y * P(f"{name}/weight").reshape(aff) + P(f"{name}/bias").reshape(aff)
@@ -120,7 +121,7 @@ def nn_layer_norm(P, name, x, eps=1e-5):
     """burn nn::LayerNorm (third-party): biased variance, eps inside sqrt, affine."""
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
-    return (x - mu) / (var + eps).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
+    return (x - mu) / (var + P.norm_eps.get(name, eps)).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
 
 
 def gelu_erf(x):

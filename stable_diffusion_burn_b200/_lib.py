@@ -38,6 +38,8 @@ SIGNATURES = [
     ("sdb_latent_to_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _u8p]),
     ("sdb_sample_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_double, C.c_int, _f32p,
                                    C.c_uint64, C.c_int, C.c_int, _u8p]),
+    ("sdb_load_dump_dir", C.c_int, [_ctx, C.c_char_p]),
+    ("sdb_read_dump_tensor", C.c_int64, [C.c_char_p, C.c_int, C.POINTER(C.c_int64), _f32p, C.c_int64]),
     ("sdb_clip_forward", C.c_int, [_ctx, C.POINTER(C.c_int32), C.c_int, C.c_int, _f32p]),
     ("sdb_clip_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("sdb_unet_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -162,6 +164,9 @@ class Context:
         out = np.empty_like(x)
         self.check(self.lib.sdb_unet_forward(self.h, ptr(x), int(t), ptr(context), n, H, W, L, ptr(out)))
         return out
+
+    def load_dump_dir(self, path):
+        self.check(self.lib.sdb_load_dump_dir(self.h, os.fsencode(path)))
 
     def clip_forward(self, tokens):
         t = np.ascontiguousarray(tokens, dtype=np.int32)

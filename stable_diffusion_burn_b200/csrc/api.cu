@@ -125,8 +125,33 @@ int sdb_get_tensor(sdb_ctx* ctx, const char* name, float* host, int64_t count) {
   API_END
 }
 
+int sdb_load_dump_dir(sdb_ctx* ctx, const char* path) {
+  API_BEGIN(ctx)
+  model_load_dump_dir(c, path);
+  API_END
+}
+
+int64_t sdb_read_dump_tensor(const char* file, int ndim, int64_t* dims, float* data, int64_t capacity) {
+  try {
+    SDB_CHECK(file && dims && ndim >= 1 && ndim <= 4, "bad argument");
+    std::vector<float> payload;
+    int64_t d[4];
+    const long long count = dump_tensor_read(file, ndim, d, payload);
+    for (int i = 0; i < ndim; ++i) dims[i] = d[i];
+    if (data) {
+      SDB_CHECK(capacity >= count, "buffer too small");
+      std::memcpy(data, payload.data() + ndim, (size_t)count * sizeof(float));
+    }
+    return count;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 int sdb_init_synthetic(sdb_ctx* ctx, uint32_t seed) {
   API_BEGIN(ctx)
+  c.norm_eps.clear();
   model_init_synthetic(c, seed);
   c.finalized = false;
   API_END

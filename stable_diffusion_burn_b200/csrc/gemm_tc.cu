@@ -411,8 +411,7 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
     attr_set = true;
   }
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;

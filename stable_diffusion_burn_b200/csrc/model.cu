@@ -64,7 +64,12 @@ static void pack_lin(Ctx& c, LinW& w) {
   w.packed.N = w.out, w.packed.K = w.in;
   pack_linear_launch(mptr(c, w.wi), w.in, w.out, w.packed.p, 0, c.stream);
 }
-static void pack_norm(Ctx& c, NormW& n) { n.gamma = mptr(c, n.gi), n.beta = mptr(c, n.bi); }
+static void pack_norm(Ctx& c, NormW& n) {
+  n.gamma = mptr(c, n.gi), n.beta = mptr(c, n.bi);
+  const std::string& g = c.tensors[n.gi].name;
+  auto it = c.norm_eps.find(g.substr(0, g.rfind('/')));
+  n.eps = it == c.norm_eps.end() ? 1e-5f : it->second;
+}
 
 // [rows = heads*dpad][in]: head h occupies rows h*dpad .. h*dpad+d (pad rows stay zero)
 static void pack_heads(Ctx& c, const LinW& src, int heads, int d, int dpad, Half2Ptr dst, int row_offset) {
@@ -257,7 +262,7 @@ struct Fwd {
     const int HW = x0.H * x0.W;
     float* part = c.work.get<float>(gn_fused_partial_floats(nb, HW));
     KernelScope ks(c, KC_PREP, 0, (double)nb * HW * C * (8.0 + 2.0 + (lo ? 2.0 : 0.0)));
-    gn_fused_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, 1e-5f,
+    gn_fused_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, nw.eps,
                     a.p, sums, part, tk, tk + nb, c.stream);
     return a;
   }
@@ -351,7 +356,7 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   Half2Ptr o16 = f.half2((size_t)Mt * C, lo);
   auto ln = [&](const NormW& nw) {
     KernelScope ks(c, KC_LAYERNORM, 0, (double)Mt * C * 6.0);
-    layernorm_launch(y, (int)Mt, C, nw.gamma, nw.beta, 1e-5f, l16, nullptr, c.stream);
+    layernorm_launch(y, (int)Mt, C, nw.gamma, nw.beta, nw.eps, l16, nullptr, c.stream);
   };
   // ---- self attention: x += out(attn(q,k,v = LN1(x)))
   ln(s.ln1);
@@ -582,7 +587,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   {
     double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 320 * 4);
-    conv3x3_small_cout_launch(x.p, f.nb, H, W, 320, sums, m.norm_out.gamma, m.norm_out.beta, 1e-5f, m.conv_out.w_small,
+    conv3x3_small_cout_launch(x.p, f.nb, H, W, 320, sums, m.norm_out.gamma, m.norm_out.beta, m.norm_out.eps, m.conv_out.w_small,
                               m.conv_out.bias, 4, io.out, c.stream);
   }
   c.work.off = mark0;
@@ -704,7 +709,7 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   {
     double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 128 * 3);
-    conv3x3_small_cout_launch(x.p, f.nb, H, W, 128, sums, m.vae_norm_out.gamma, m.vae_norm_out.beta, 1e-5f,
+    conv3x3_small_cout_launch(x.p, f.nb, H, W, 128, sums, m.vae_norm_out.gamma, m.vae_norm_out.beta, m.vae_norm_out.eps,
                               m.vae_conv_out.w_small, m.vae_conv_out.bias, 3, d_img, c.stream);
   }
   c.work.off = mark0;
@@ -1009,7 +1014,7 @@ void model_clip_forward_dev(Ctx& c, const int* d_tok, int n, int L, float* d_out
   }
   auto ln = [&](const NormW& nw, Half2Ptr o, float* o32) {
     KernelScope ks(c, KC_LAYERNORM);
-    layernorm_launch(x, Mr, D, nw.gamma, nw.beta, 1e-5f, o, o32, c.stream);
+    layernorm_launch(x, Mr, D, nw.gamma, nw.beta, nw.eps, o, o32, c.stream);
   };
   for (ClipBlockW& cb : m.clip.blocks) {
     ln(cb.attn_ln, l16, nullptr);

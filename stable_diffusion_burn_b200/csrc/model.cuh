@@ -23,6 +23,10 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
                       cudaStream_t caller);
 void model_clip_forward_dev(Ctx& c, const int* d_tokens, int n, int L, float* d_out, cudaStream_t caller);
 void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out);
+// dump-dir reader (dumpdir.cu)
+bool npy_read_f32(const std::string& file, std::vector<float>& out);
+long long dump_tensor_read(const std::string& file, int ndim, int64_t* dims, std::vector<float>& payload);
+void model_load_dump_dir(Ctx& c, const char* root);
 void model_test_attention(Ctx& c, const float* q, const float* k, const float* v, int n, int Nq, int Nk, int C, int heads,
                           float* out);
 

@@ -7,7 +7,6 @@
 
 namespace sdb {
 
-enum { K_CONV_W = 0, K_CONV_B, K_LIN_W, K_LIN_B, K_NORM_G, K_NORM_B, K_SCHED, K_EMB };
 
 // ------------------------------------------------------------------ registry builder
 struct Builder {
@@ -28,8 +27,14 @@ struct Builder {
     c.tensors.push_back(t);
     return (int)c.tensors.size() - 1;
   }
-  void conv(ConvW& w, const std::string& name, int cin, int cout, int k) {
+  void scalar(const std::string& rel, float v) { c.meta.push_back(MetaCheck{rel, {v}, false}); }
+  void pair(const std::string& rel, float a, float b) { c.meta.push_back(MetaCheck{rel, {a, b}, false}); }
+  // the files save_conv2d writes beside weight/bias (python/save.py:52-68, read by load_conv2d load.rs:118-160)
+  void conv(ConvW& w, const std::string& name, int cin, int cout, int k, int stride = 1) {
     w.cin = cin, w.cout = cout, w.k = k;
+    pair(name + "/stride", (float)stride, (float)stride), pair(name + "/padding", (float)(k / 2), (float)(k / 2));
+    pair(name + "/dilation", 1.f, 1.f), pair(name + "/kernel_size", (float)k, (float)k);
+    scalar(name + "/n_group", 1.f), scalar(name + "/n_channels_in", (float)cin), scalar(name + "/n_channels_out", (float)cout);
     w.wi = add(name + "/weight", {cout, cin, k, k}, K_CONV_W, cin * k * k);
     w.bi = add(name + "/bias", {cout}, K_CONV_B, cin * k * k);
   }
@@ -37,9 +42,12 @@ struct Builder {
     w.in = in, w.out = out;
     w.wi = add(name + "/weight", {in, out}, K_LIN_W, in);
     if (bias) w.bi = add(name + "/bias", {out}, K_LIN_B, in);
+    else c.meta.push_back(MetaCheck{name + "/bias", {}, true});
   }
-  void norm(NormW& w, const std::string& name, int ch) {
+  // group = true: GroupNorm(32) (save_group_norm save.py:30-38); false: LayerNorm (save_layer_norm :24-28)
+  void norm(NormW& w, const std::string& name, int ch, bool group = true) {
     w.c = ch;
+    if (group) c.group_norms.insert(name), scalar(name + "/n_group", 32.f), scalar(name + "/n_channel", (float)ch);
     w.gi = add(name + "/weight", {ch}, K_NORM_G, ch);
     w.bi = add(name + "/bias", {ch}, K_NORM_B, ch);
   }
@@ -54,6 +62,7 @@ struct Builder {
     if (r.has_skip) conv(r.skip, name + "/skip_connection", cin, cout, 1);
   }
   void mha(AttnW& a, const std::string& name, int ch, int cctx) {  // unet/mod.rs:601-630
+    scalar(name + "/n_head", 8.f);  // unet/load.rs:46
     lin(a.query, name + "/query", ch, ch, false);
     lin(a.key, name + "/key", cctx, ch, false);
     lin(a.value, name + "/value", cctx, ch, false);
@@ -65,11 +74,11 @@ struct Builder {
     norm(s.norm, name + "/norm", ch);
     conv(s.proj_in, name + "/proj_in", ch, ch, 1);
     const std::string t = name + "/transformer";
-    norm(s.ln1, t + "/norm1", ch);
+    norm(s.ln1, t + "/norm1", ch, false);
     mha(s.attn1, t + "/attn1", ch, ch);
-    norm(s.ln2, t + "/norm2", ch);
+    norm(s.ln2, t + "/norm2", ch, false);
     mha(s.attn2, t + "/attn2", ch, 768);
-    norm(s.ln3, t + "/norm3", ch);
+    norm(s.ln3, t + "/norm3", ch, false);
     lin(s.geglu, t + "/mlp/geglu/proj", ch, 8 * ch);
     lin(s.ff, t + "/mlp/lin", 4 * ch, ch);
     conv(s.proj_out, name + "/proj_out", ch, ch, 1);
@@ -104,7 +113,7 @@ static void build_block(Builder& b, UNetBlockW& blk, const std::string& name, co
   switch (s.kind) {
     case BK_CONV:
     case BK_DOWN:
-      b.conv(blk.conv, name, s.cin, s.cout, 3);
+      b.conv(blk.conv, name, s.cin, s.cout, 3, s.kind == BK_DOWN ? 2 : 1);
       break;
     case BK_R:
       b.resblock(blk.res, name, s.cin, s.cout);
@@ -176,6 +185,7 @@ void model_create(Ctx& c) {
     m->dec[i].has_up = i != 3;
     if (m->dec[i].has_up) b.conv(m->dec[i].up, bn + "/upsampler", dec_ch[i][1], dec_ch[i][1], 3);
   }
+  b.scalar(d + "/n_block", 4.f);  // autoencoder/load.rs:139
   b.norm(m->vae_norm_out, d + "/norm_out", 128);
   b.conv(m->vae_conv_out, d + "/conv_out", 128, 3, 3);
   // ---- CLIP text encoder (clip/mod.rs:25-44, CLIPConfig::new(49408,768,12,77,12))
@@ -185,16 +195,18 @@ void model_create(Ctx& c) {
   for (int i = 0; i < 12; ++i) {
     ClipBlockW& cb = m->clip.blocks[i];
     const std::string bn = "clip/blocks/" + std::to_string(i);
-    b.norm(cb.attn_ln, bn + "/attn_ln", 768);
+    b.norm(cb.attn_ln, bn + "/attn_ln", 768, false);
+    b.scalar(bn + "/attn/n_head", 12.f);  // clip/load.rs:32
     b.lin(cb.query, bn + "/attn/query", 768, 768);
     b.lin(cb.key, bn + "/attn/key", 768, 768);
     b.lin(cb.value, bn + "/attn/value", 768, 768);
     b.lin(cb.out, bn + "/attn/out", 768, 768);
-    b.norm(cb.mlp_ln, bn + "/mlp_ln", 768);
+    b.norm(cb.mlp_ln, bn + "/mlp_ln", 768, false);
     b.lin(cb.fc1, bn + "/mlp/fc1", 768, 3072);
     b.lin(cb.fc2, bn + "/mlp/fc2", 3072, 768);
   }
-  b.norm(m->clip.ln_final, "clip/layer_norm", 768);
+  b.norm(m->clip.ln_final, "clip/layer_norm", 768, false);
+  b.scalar("clip/n_layer", 12.f);  // clip/load.rs:73
   // ---- sampler schedule (stablediffusion/mod.rs:44)
   m->alphas_i = b.add("alpha_cumulative_products", {1000}, K_SCHED, 1);
 

@@ -27,6 +27,7 @@ struct NormW {
   int gi = -1, bi = -1;
   float* gamma = nullptr;
   float* beta = nullptr;
+  float eps = 1e-5f;  // a dump-dir's eps.npy overrides it (load_group_norm / load_layer_norm)
 };
 struct ResBlockW {
   int cin = 0, cout = 0;

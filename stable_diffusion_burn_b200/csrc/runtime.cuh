@@ -2,6 +2,7 @@
 #pragma once
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -24,13 +25,14 @@ struct Arena {
   void reset() { off = 0; }
 };
 
+enum TensorKind : int { K_CONV_W = 0, K_CONV_B, K_LIN_W, K_LIN_B, K_NORM_G, K_NORM_B, K_SCHED, K_EMB };
 struct TensorInfo {
   std::string name;
   int64_t dims[4] = {1, 1, 1, 1};
   int ndim = 0;
   size_t offset = 0;  // float offset in the master arena
   int64_t count = 0;
-  int kind = 0;       // 0 conv_w 1 conv_b 2 lin_w 3 lin_b 4 norm_g 5 norm_b 6 schedule
+  int kind = 0;       // TensorKind
   int fan_in = 1;
 };
 
@@ -79,6 +81,14 @@ struct Epilogue {
   int ldc16 = 0;  // 0 -> N (or N/2 for geglu)
 };
 
+// a configuration scalar / small vector the reference's loaders read beside the tensors (dump-dir, dumpdir.cu):
+// relpath (no ".npy") and the values it must hold for the compiled topology
+struct MetaCheck {
+  std::string relpath;
+  std::vector<float> values;
+  bool must_be_absent = false;  // e.g. a bias file on a bias-less Linear
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -88,6 +98,9 @@ struct Ctx {
   std::vector<TensorInfo> tensors;
   std::unordered_map<std::string, int> index;
   bool finalized = false;
+  std::vector<MetaCheck> meta;                       // dump-dir configuration files to validate
+  std::unordered_set<std::string> group_norms;       // norm dirs that are GroupNorm (optional weight/bias on disk)
+  std::unordered_map<std::string, float> norm_eps;   // per-norm eps read from a dump-dir (default 1e-5)
   // options
   int opt_precision = 0;  // 0 = per-layer policy, 1/2/3 = force
   int opt_graphs = 1;
