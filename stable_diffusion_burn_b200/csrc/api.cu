@@ -62,7 +62,7 @@ int sdb_create(int device, sdb_ctx** out) {
     h->c.device = device;
     h->c.debug_sync = getenv("SDB_DEBUG_SYNC") && atoi(getenv("SDB_DEBUG_SYNC")) != 0;
     if (getenv("SDB_CLUSTER")) h->c.opt_cluster = atoi(getenv("SDB_CLUSTER"));
-    if (getenv("SDB_PDL")) g_pdl_enabled = atoi(getenv("SDB_PDL")) != 0;
+    if (getenv("SDB_PDL")) g_pdl_enabled = atoi(getenv("SDB_PDL")) != 0, g_pdl_late = atoi(getenv("SDB_PDL")) == 2;
     if (getenv("SDB_PAIR_BN256")) h->c.opt_pair_bn256 = atoi(getenv("SDB_PAIR_BN256"));
     SDB_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
     model_create(h->c);
@@ -267,6 +267,8 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_cluster = value;
   else if (k == "pair_bn256")
     c.opt_pair_bn256 = value;
+  else if (k == "raw16")
+    c.opt_raw16 = value;
   else
     throw Error("unknown option: " + k);
   model_invalidate_graphs(c);

@@ -36,6 +36,7 @@ struct Error : std::runtime_error {
 // Programmatic dependent launch (PDL): a kernel launched with the attribute may start (launch latency, CTA
 // scheduling, its prologue up to pdl_wait()) while its predecessor on the stream is still draining.
 extern bool g_pdl_enabled;
+extern int g_pdl_late;
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

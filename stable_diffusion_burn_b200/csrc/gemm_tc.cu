@@ -31,8 +31,36 @@ struct StageLayout {
   static constexpr int BYTES = A_TILES * A_TILE_BYTES + B_TILES * B_TILE_BYTES;
 };
 
+// Activation + fp32 / fp16(hi,lo) stores of 4 consecutive columns of one output row. Deliberately NOT inlined: the epilogue
+// runs once per CTA, so its cost is dominated by cold instruction fetch (ncu: stall_no_inst); one shared copy of this
+// body instead of one per unrolled row keeps the epilogue's code footprint small.
+__device__ __noinline__ void epilogue_store(float4 f, unsigned int o32, unsigned int o16, float* out_f32, __half* out_f16,
+                                            __half* out_f16_lo, int act) {
+  if (act == 1) {
+    f.x = __fdividef(f.x, 1.0f + __expf(-1.702f * f.x)), f.y = __fdividef(f.y, 1.0f + __expf(-1.702f * f.y));
+    f.z = __fdividef(f.z, 1.0f + __expf(-1.702f * f.z)), f.w = __fdividef(f.w, 1.0f + __expf(-1.702f * f.w));
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o32) = f;
+  if (out_f16) {
+    __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
+    *reinterpret_cast<uint2*>(out_f16 + o16) = *reinterpret_cast<uint2*>(h);
+    if (out_f16_lo) {
+      const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+      __half2 l[2] = {__floats2half2_rn(f.x - f0.x, f.y - f0.y), __floats2half2_rn(f.z - f1.x, f.w - f1.y)};
+      *reinterpret_cast<uint2*>(out_f16_lo + o16) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+}
+
+// Variants whose pipeline fits twice in an SM's shared memory are launched two CTAs per SM (<= 102 registers per thread);
+// the others own the SM and may use the whole register file.
 template <int BN, int PASSES, int STAGES, int CG>
-__global__ void __launch_bounds__(320, 2)
+constexpr int min_ctas_per_sm() {
+  return STAGES * StageLayout<BN, PASSES, CG>::BYTES <= 108 * 1024 ? 2 : 1;
+}
+
+template <int BN, int PASSES, int STAGES, int CG>
+__global__ void __launch_bounds__(320, min_ctas_per_sm<BN, PASSES, STAGES, CG>())
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using L = StageLayout<BN, PASSES, CG>;
   constexpr bool TWO = CG == 2;
@@ -46,7 +74,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_trigger();  // the next kernel of the stream may begin its own prologue
+  long long* const dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  if (!p.pdl_late) pdl_trigger();  // the next kernel of the stream may begin its own prologue
 
   // ---- tile coordinates
   int mt = blockIdx.x;
@@ -94,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
@@ -124,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           tma_load_2d_2sm(sb, &maps.b[0], fb, it * BK, col0 + crank * (BN / 2));
           if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &maps.b[1], fb, it * BK, col0 + crank * (BN / 2));
         }
+        if (dbg && it == it_begin) dbg[2] = clock64();
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
@@ -138,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     for (int it = it_begin; leader && it < it_end; ++it) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
+      if (dbg && lane == 0 && it == it_begin) dbg[3] = clock64();
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * L::BYTES);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
@@ -166,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           umma_commit(&empty_bar[s]);                    // frees the smem slot when these MMAs retire
           if (it == it_end - 1) umma_commit(accum_bar);  // accumulator complete
         }
+        if (dbg && it == it_end - 1) dbg[4] = clock64();
       }
       __syncwarp();
       if (++s == STAGES) {
@@ -190,15 +224,54 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     // output row index (< 2^31 rows); -1 marks a row outside the tensor
     const int m = row_ok ? ((pn * p.OH + phh * p.os + p.oa) * p.OW + pw * p.os + p.ob) : -1;
 
+    // ---- work that needs no accumulator, done while the main loop runs: the element offsets of the 8 rows this lane
+    // serves in every column chunk (rr = 4 i + sub), the bias of each chunk, and the first chunk's addends (residual or
+    // time-embedding row; run_gemm guarantees at most one of them). The epilogue is a chain of L2 round trips
+    // (~650 cycles each, measured with clock64 stamps): everything issued here is off that chain.
+    const int sub = lane >> 3;          // row within a group of 4
+    const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
+    constexpr int NCHUNK = (BN + 63) / 64;
+    int mr8[8], ao[8];
+    float4 bvs[NCHUNK], ad[8];
+    const float* ad_ptr = p.residual ? p.residual : p.rowbias;
+    const bool plain = p.split_k == 1 && !p.geglu;
+    {
+      const bool use_res = p.residual != nullptr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const int mr = __shfl_sync(0xffffffffu, m, rr);
+        const int pnr = __shfl_sync(0xffffffffu, pn, rr);
+        mr8[i] = mr;
+        ao[i] = use_res ? mr * p.ldc : pnr * p.N;
+        ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < NCHUNK; ++j) {
+        const int col = col0 + half * 32 + j * 64 + cq;
+        bvs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (plain && p.bias && half * 32 + j * 64 < BN && col < p.N) bvs[j] = *reinterpret_cast<const float4*>(p.bias + col);
+      }
+    }
+    auto issue_addends = [&](int col) {
+      if (ad_ptr == nullptr || col >= p.N) return;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mr8[i] >= 0) ad[i] = *reinterpret_cast<const float4*>(ad_ptr + (unsigned)(ao[i] + col));
+    };
+    // the residual may be produced by the previous kernel (always complete: stream order) or be this launch's own
+    // output buffer written by an EARLIER launch (in-place accumulate): both are safe to read before the MMAs finish
+    const bool pre_issued = plain;
+    if (pre_issued) issue_addends(col0 + half * 32 + cq);
+
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (p.pdl_late) pdl_trigger();
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
     constexpr uint32_t TROW = 144;                                   // padded row pitch of the staging tile (bytes)
     const uint32_t tile_s = smem_u32(smem) + (warp - 2) * (32 * TROW);  // one 32-row tile per warp (36.9 KB in all)
     const uint32_t tile2_s = tile_s + 8 * 32 * TROW;                     // second bank, GEGLU only (x | gate)
-
-    const int sub = lane >> 3;          // row within a group of 4
-    const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
 
     auto stage = [&](uint32_t t, const uint32_t (&v)[32]) {
 #pragma unroll
@@ -215,33 +288,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                    : "memory");
       return f;
     };
-    // bias / time-embedding row / residual / fp32 + fp16(hi,lo) stores for 4 consecutive columns of one output row
-    auto finish = [&](float4 f, int mr, int pnr, int col, const float4& bv) {
-      f.x += bv.x, f.y += bv.y, f.z += bv.z, f.w += bv.w;
-      if (p.rowbias) {
-        const float4 b = *reinterpret_cast<const float4*>(p.rowbias + (size_t)pnr * p.N + col);
-        f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
-      }
-      const size_t o32 = (size_t)mr * p.ldc + col;
-      if (p.residual) {
-        const float4 b = *reinterpret_cast<const float4*>(p.residual + o32);
-        f.x += b.x, f.y += b.y, f.z += b.z, f.w += b.w;
-      }
-      if (p.act == 1) {
-        f.x = f.x / (1.0f + __expf(-1.702f * f.x)), f.y = f.y / (1.0f + __expf(-1.702f * f.y));
-        f.z = f.z / (1.0f + __expf(-1.702f * f.z)), f.w = f.w / (1.0f + __expf(-1.702f * f.w));
-      }
-      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o32) = f;
-      if (p.out_f16) {
-        __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
-        const size_t o = (size_t)mr * p.ldc16 + col;
-        *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
-        if (p.out_f16_lo) {
-          const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-          __half2 l[2] = {__floats2half2_rn(f.x - f0.x, f.y - f0.y), __floats2half2_rn(f.z - f1.x, f.w - f1.y)};
-          *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
-        }
-      }
+    // element offsets fit 32 bits (run_gemm checks rows * ld < 2^31): one IMAD per row instead of 64-bit address chains
+    auto store_out = [&](float4 f, int mr, int col) {
+      epilogue_store(f, (unsigned)(mr * p.ldc + col), (unsigned)(mr * p.ldc16 + col), p.out_f32, p.out_f16, p.out_f16_lo, p.act);
     };
 
     if (p.split_k > 1) {
@@ -284,20 +333,41 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int r0 = blockIdx.z * rows_per, r1 = min(BM, r0 + rows_per);
         constexpr int C4 = BN / 4;
         const int te = threadIdx.x - 64;
+#pragma unroll 1
         for (int idx = te; idx < (r1 - r0) * C4; idx += 256) {
           const int rl = r0 + idx / C4;
           const int col = col0 + (idx % C4) * 4;
           const int qw = w0 + rl % p.TW, qh = h0 + (rl / p.TW) % p.TH, qn = n0 + rl / (p.TW * p.TH);
           if (qw < p.W && qh < p.H && qn < p.nimg && col < p.N) {
             const int mr = (qn * p.OH + qh * p.os + p.oa) * p.OW + qw * p.os + p.ob;
+            // the addends first, then the partials four at a time: independent loads in flight together, summed in z order
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rb = bv, rs = bv;
+            if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
+            if (p.rowbias) rb = *reinterpret_cast<const float4*>(p.rowbias + (size_t)qn * p.N + col);
+            if (p.residual) rs = *reinterpret_cast<const float4*>(p.residual + (size_t)mr * p.ldc + col);
+            const float* wp = p.ws + (size_t)mr * p.N + col;
+            const size_t zs = Mtot * p.N;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < p.split_k; ++z) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)z * Mtot + mr) * p.N + col));
+            int z = 0;
+#pragma unroll 1
+            for (; z + 4 <= p.split_k; z += 4) {
+              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)z * zs));
+              const float4 v1 = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)(z + 1) * zs));
+              const float4 v2 = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)(z + 2) * zs));
+              const float4 v3 = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)(z + 3) * zs));
+              acc.x += v0.x, acc.y += v0.y, acc.z += v0.z, acc.w += v0.w;
+              acc.x += v1.x, acc.y += v1.y, acc.z += v1.z, acc.w += v1.w;
+              acc.x += v2.x, acc.y += v2.y, acc.z += v2.z, acc.w += v2.w;
+              acc.x += v3.x, acc.y += v3.y, acc.z += v3.z, acc.w += v3.w;
+            }
+#pragma unroll 1
+            for (; z < p.split_k; ++z) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(wp + (size_t)z * zs));
               acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             }
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
-            finish(acc, mr, qn, col, bv);
+            acc.x += bv.x + rb.x + rs.x, acc.y += bv.y + rb.y + rs.y;
+            acc.z += bv.z + rb.z + rs.z, acc.w += bv.w + rb.w + rs.w;
+            store_out(acc, mr, col);
           }
         }
       }
@@ -325,51 +395,65 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         __syncwarp();
         const float4 bx = *reinterpret_cast<const float4*>(p.bias + col0 + c + cq);
         const float4 bg = *reinterpret_cast<const float4*>(p.bias + col0 + HB + c + cq);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub;
           const int mr = __shfl_sync(0xffffffffu, m, rr);
           if (mr >= 0) {
             const float4 tx = unstage(tile_s, rr), tg = unstage(tile2_s, rr);
-            const float y0 = (tx.x + bx.x) * gelu_erf_fast(tg.x + bg.x);
-            const float y1 = (tx.y + bx.y) * gelu_erf_fast(tg.y + bg.y);
-            const float y2 = (tx.z + bx.z) * gelu_erf_fast(tg.z + bg.z);
-            const float y3 = (tx.w + bx.w) * gelu_erf_fast(tg.w + bg.w);
-            __half2 h[2] = {__floats2half2_rn(y0, y1), __floats2half2_rn(y2, y3)};
-            const size_t o = (size_t)mr * p.ldc16 + ocol0 + c + cq;
-            *reinterpret_cast<uint2*>(p.out_f16 + o) = *reinterpret_cast<uint2*>(h);
-            if (p.out_f16_lo) {
-              const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-              __half2 l[2] = {__floats2half2_rn(y0 - f0.x, y1 - f0.y), __floats2half2_rn(y2 - f1.x, y3 - f1.y)};
-              *reinterpret_cast<uint2*>(p.out_f16_lo + o) = *reinterpret_cast<uint2*>(l);
-            }
+            float4 y;
+            y.x = (tx.x + bx.x) * gelu_erf_fast(tg.x + bg.x);
+            y.y = (tx.y + bx.y) * gelu_erf_fast(tg.y + bg.y);
+            y.z = (tx.z + bx.z) * gelu_erf_fast(tg.z + bg.z);
+            y.w = (tx.w + bx.w) * gelu_erf_fast(tg.w + bg.w);
+            epilogue_store(y, 0u, (unsigned)(mr * p.ldc16 + ocol0 + c + cq), nullptr, p.out_f16, p.out_f16_lo, 0);
           }
         }
         __syncwarp();
       }
     } else {
-#pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
-        uint32_t v[32];
-        tmem_ld32(trow + c, v);
-        tmem_ld_wait();
-        stage(tile_s, v);
-        __syncwarp();
-        const int col = col0 + c + cq;
-        const bool col_ok = col < p.N;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + col);
+      constexpr int NCH = (BN + 63) / 64;  // column chunks per warp (the two warps of a lane quarter interleave them)
+      if (!pre_issued) issue_addends(col0 + half * 32 + cq);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + sub;
-          const int mr = __shfl_sync(0xffffffffu, m, rr);
-          const int pnr = p.rowbias ? __shfl_sync(0xffffffffu, pn, rr) : 0;
-          if (mr >= 0 && col_ok) finish(unstage(tile_s, rr), mr, pnr, col, bv);
+      for (int j = 0; j < NCH; ++j) {
+        const int c = half * 32 + j * 64;
+        if (c < BN) {
+          uint32_t v[32];
+          tmem_ld32(trow + c, v);
+          tmem_ld_wait();
+          stage(tile_s, v);
+          __syncwarp();
+          const int col = col0 + c + cq;
+          if (col < p.N) {
+            const uint32_t tl = tile_s + sub * TROW + cq * 4;
+#pragma unroll
+            for (int b4 = 0; b4 < 2; ++b4) {
+              float4 t[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(t[i].x), "=f"(t[i].y), "=f"(t[i].z), "=f"(t[i].w)
+                             : "r"(tl + (b4 * 4 + i) * 4 * TROW)
+                             : "memory");
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = b4 * 4 + i;
+                if (mr8[k] < 0) continue;
+                float4 f = t[i];
+                f.x += bvs[j].x + ad[k].x, f.y += bvs[j].y + ad[k].y, f.z += bvs[j].z + ad[k].z, f.w += bvs[j].w + ad[k].w;
+                epilogue_store(f, (unsigned)(mr8[k] * p.ldc + col), (unsigned)(mr8[k] * p.ldc16 + col), p.out_f32, p.out_f16,
+                               p.out_f16_lo, p.act);
+              }
+            }
+          }
+          __syncwarp();
+          // the next chunk's addends travel while its accumulator columns are read and staged
+          if (j + 1 < NCH && c + 64 < BN) issue_addends(col0 + c + 64 + cq);
         }
-        __syncwarp();
       }
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
   }
 
   if (TWO)
@@ -383,6 +467,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     else
       tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 // ------------------------------------------------------------------ launcher

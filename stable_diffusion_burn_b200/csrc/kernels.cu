@@ -194,19 +194,18 @@ void prep_operand_launch(const float* x0, int C0, const float* x1, int C1, int n
 }
 
 // ============================================================ fused GroupNorm: statistics + apply in ONE launch
-// Phase 1: per-CTA group partials of the CTA's pixel chunk (fixed-order, deterministic); the last CTA of an image
-// folds them and raises a flag. Phase 2 (after an in-kernel wait on that flag): normalise + SiLU + fp16 hi/lo split
-// of the same chunk (second read hits L2). The grid never exceeds 4 CTAs per SM, so every CTA is resident and the
-// wait cannot deadlock.
+// Phase 1: per-CTA group partials of the CTA's pixel chunk (fixed-order, deterministic), published to global memory.
+// After an in-kernel rendezvous of the image's CTAs every CTA folds all partials (same order everywhere). Phase 2:
+// normalise + SiLU + fp16 hi/lo split of the same chunk (second read hits L2). The grid never exceeds 4 CTAs per SM,
+// so every CTA is resident and the wait cannot deadlock.
 __global__ void __launch_bounds__(256)
 gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int H, int W, int pix_per_cta,
                 int silu, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                __half* __restrict__ out_hi, __half* __restrict__ out_lo, double* __restrict__ sums,
-                float* __restrict__ partials, unsigned int* __restrict__ tickets, unsigned int* __restrict__ flags) {
+                __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ partials,
+                unsigned int* __restrict__ tickets) {
   pdl_enter();
   extern __shared__ float s_dyn[];  // scale[C], shift[C]
   __shared__ float s_pair[2][1280];
-  __shared__ bool s_last;
   const int n = blockIdx.y;
   const int C = C0 + C1, gs = C / 32, HW = H * W;
   const int p0 = blockIdx.x * pix_per_cta;
@@ -259,37 +258,38 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1u) == (unsigned)(chunks - 1);
-  __syncthreads();
-  if (s_last) {
-    // fold the per-CTA partials: 4 threads per statistic, each a contiguous quarter of the chunks (fixed order)
-    __shared__ double s_fold[4][64];
-    __threadfence();
-    {
-      const int stat = threadIdx.x & 63, part = threadIdx.x >> 6;
-      const int per = (chunks + 3) / 4;
-      const int c0 = part * per, c1 = min(chunks, c0 + per);
-      double acc = 0.0;
-#pragma unroll 4
-      for (int ch = c0; ch < c1; ++ch) acc += (double)__ldcg(&partials[((size_t)n * chunks + ch) * 64 + stat]);
-      s_fold[part][stat] = acc;
-    }
-    __syncthreads();
-    if (threadIdx.x < 64)
-      sums[(size_t)n * 64 + threadIdx.x] = ((s_fold[0][threadIdx.x] + s_fold[1][threadIdx.x]) + s_fold[2][threadIdx.x]) + s_fold[3][threadIdx.x];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicExch(&flags[n], 1u);
-  }
-  // ---- wait for the image's statistics
+  // ---- rendezvous of the image's CTAs (all co-resident), then EVERY CTA folds the partials itself in the same fixed
+  // order: no single-CTA serial tail and no second flag round trip; the result is identical in every CTA.
   if (threadIdx.x == 0) {
+    atomicAdd(&tickets[n], 1u);
     const long long t0 = clock64();
-    while (atomicAdd(&flags[n], 0u) == 0u) {
-      __nanosleep(100);
+    while (atomicAdd(&tickets[n], 0u) < (unsigned)chunks) {
+      __nanosleep(64);
       if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost CTA becomes a launch failure, not a hung GPU
     }
     __threadfence();
   }
+  __syncthreads();
+  __shared__ double s_fold[4][64];
+  __shared__ double s_sum[64];
+  {
+    const int stat = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int per = (chunks + 3) / 4;
+    const int c0 = part * per, c1 = min(chunks, c0 + per);
+    const float* src = partials + (size_t)n * chunks * 64 + stat;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int ch = c0;
+    for (; ch + 3 < c1; ch += 4) {
+      const float v0 = __ldcg(src + (size_t)ch * 64), v1 = __ldcg(src + (size_t)(ch + 1) * 64);
+      const float v2 = __ldcg(src + (size_t)(ch + 2) * 64), v3 = __ldcg(src + (size_t)(ch + 3) * 64);
+      a0 += (double)v0, a1 += (double)v1, a2 += (double)v2, a3 += (double)v3;
+    }
+    for (; ch < c1; ++ch) a0 += (double)__ldcg(src + (size_t)ch * 64);
+    s_fold[part][stat] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64)
+    s_sum[threadIdx.x] = ((s_fold[0][threadIdx.x] + s_fold[1][threadIdx.x]) + s_fold[2][threadIdx.x]) + s_fold[3][threadIdx.x];
   __syncthreads();
   // ---- phase 2
   float* s_scale = s_dyn;
@@ -298,7 +298,7 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
     const double inv_cnt = 1.0 / ((double)gs * HW);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / gs;
-      const double sm = __ldcg(&sums[((size_t)n * 32 + g) * 2 + 0]), sq = __ldcg(&sums[((size_t)n * 32 + g) * 2 + 1]);
+      const double sm = s_sum[g * 2 + 0], sq = s_sum[g * 2 + 1];
       const double mean = sm * inv_cnt;
       double var = sq * inv_cnt - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -336,15 +336,14 @@ static int gn_fused_pix(int n, int HW) {
 size_t gn_fused_partial_floats(int n, int HW) { return (size_t)n * ceil_div(HW, gn_fused_pix(n, HW)) * 64; }
 
 void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int silu, const float* gamma,
-                     const float* beta, float eps, Half2Ptr out, double* sums, float* partials, unsigned int* tickets,
-                     unsigned int* flags, cudaStream_t st) {
+                     const float* beta, float eps, Half2Ptr out, float* partials, unsigned int* tickets, cudaStream_t st) {
   const int C = C0 + C1, HW = H * W;
   SDB_CHECK(C % 64 == 0 && C0 % 8 == 0 && C <= 2560, "GroupNorm channels");
   const int pix = gn_fused_pix(n, HW);
   dim3 grid(ceil_div(HW, pix), n);
   SDB_CHECK((long long)grid.x * grid.y <= 592, "fused GroupNorm grid must stay co-resident");
   launch_k(gn_fused_kernel, grid, dim3(256), (size_t)2 * C * sizeof(float), st, x0, C0, x1, C1, H, W, pix, silu, gamma, beta, eps, out.hi,
-           out.lo, sums, partials, tickets, flags);
+           out.lo, partials, tickets);
   SDB_CUDA(cudaGetLastError());
 }
 
@@ -498,7 +497,7 @@ void nhwc_to_nchw_launch(const float* x, int n, int C, int H, int W, float* y, c
 __global__ void __launch_bounds__(256)
 conv3x3_cin4_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w, const float* __restrict__ b,
                     int Cout, const float* __restrict__ pre_w, const float* __restrict__ pre_b, float pre_scale,
-                    float* __restrict__ y) {
+                    float* __restrict__ y, __half* __restrict__ y_hi, __half* __restrict__ y_lo) {
   pdl_enter();
   extern __shared__ float sm[];
   float* s_w = sm;                  // [36][Cout]
@@ -540,11 +539,17 @@ conv3x3_cin4_kernel(const float* __restrict__ x, int H, int W, const float* __re
     float acc = b ? b[co] : 0.f;
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc += s_in[pl * 36 + k] * s_w[k * Cout + co];
-    y[((size_t)n * HW + p) * Cout + co] = acc;
+    const size_t o = ((size_t)n * HW + p) * Cout + co;
+    y[o] = acc;
+    if (y_hi) {  // fp16 hi/lo copy for a consumer that takes this tensor as a raw GEMM operand
+      const __half h = __float2half_rn(acc);
+      y_hi[o] = h;
+      if (y_lo) y_lo[o] = __float2half_rn(acc - __half2float(h));
+    }
   }
 }
 void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* w, const float* b, int Cout,
-                         const float* pre_w, const float* pre_b, float pre_scale, float* y, cudaStream_t st) {
+                         const float* pre_w, const float* pre_b, float pre_scale, float* y, Half2Ptr y16, cudaStream_t st) {
   const size_t smem = (size_t)(36 * Cout + 32 * 36) * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -552,7 +557,8 @@ void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* 
     attr = true;
   }
   dim3 grid(ceil_div(H * W, 32), n);
-  launch_k(conv3x3_cin4_kernel, grid, dim3(256), smem, st, x_nchw, H, W, w, b, Cout, pre_w, pre_b, pre_scale, y);
+  launch_k(conv3x3_cin4_kernel, grid, dim3(256), smem, st, x_nchw, H, W, w, b, Cout, pre_w, pre_b, pre_scale, y, y16.hi,
+           y16.lo);
   SDB_CUDA(cudaGetLastError());
 }
 

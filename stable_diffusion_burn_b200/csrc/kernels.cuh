@@ -18,11 +18,10 @@ size_t gn_stats_partial_floats(int n, int HW);
 void gn_stats_launch(const float* x0, int C0, const float* x1, int C1, int n, int HW, double* sums, float* partials,
                      unsigned int* tickets, cudaStream_t st);
 // One-launch GroupNorm(+SiLU) -> fp16 hi(/lo) operand: statistics and apply fused through an in-kernel grid wait.
-// tickets/flags: [n] zeroed counters; partials: gn_fused_partial_floats(n,HW) floats of scratch.
+// tickets: [n] zeroed counters; partials: gn_fused_partial_floats(n,HW) floats of scratch.
 size_t gn_fused_partial_floats(int n, int HW);
 void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int silu, const float* gamma,
-                     const float* beta, float eps, Half2Ptr out, double* sums, float* partials, unsigned int* tickets,
-                     unsigned int* flags, cudaStream_t st);
+                     const float* beta, float eps, Half2Ptr out, float* partials, unsigned int* tickets, cudaStream_t st);
 // mode bits
 enum : int { PREP_NORM = 1, PREP_SILU = 2, PREP_UP2 = 4, PREP_PHASE2 = 8 };
 // Stages a conv/GEMM A operand: y = [silu]([groupnorm](cat(x0,x1))) -> fp16 hi(/lo).
@@ -50,7 +49,7 @@ void nhwc_to_nchw_launch(const float* x, int n, int C, int H, int W, float* y, c
 // 3x3 pad 1, Cin = 4 (NCHW fp32 input [n,4,H,W]) -> NHWC fp32 [n,H,W,Cout]; weights OIHW fp32.
 // pre: optional 1x1 4->4 conv (post_quant_conv) with scalar input scale applied to the input first.
 void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* w, const float* b, int Cout,
-                         const float* pre_w, const float* pre_b, float pre_scale, float* y, cudaStream_t st);
+                         const float* pre_w, const float* pre_b, float pre_scale, float* y, Half2Ptr y16, cudaStream_t st);
 // 3x3 pad 1, Cout <= 4, input NHWC fp32 with fused GroupNorm+SiLU; output NCHW fp32 [n,Cout,H,W];
 // weights repacked [Cout][9][C] fp32.
 void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const double* sums, const float* gamma,

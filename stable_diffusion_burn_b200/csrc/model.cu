@@ -208,6 +208,8 @@ void model_invalidate_graphs(Ctx& c) {
 // ================================================================================ forward helpers
 struct Act {
   float* p = nullptr;
+  Half2Ptr raw16;  // optional fp16 hi/lo copy of the same values, written by the producing epilogue for consumers that
+                   // read this tensor as a raw GEMM operand (skip 1x1 convs, upsample convs): no staging launch
   int n = 0, H = 0, W = 0, C = 0;
   size_t count() const { return (size_t)n * H * W * C; }
 };
@@ -237,6 +239,16 @@ struct Fwd {
     gn_stats_launch(x0, C0, x1, C1, nb, HW, sums, part, tk, c.stream);
     return sums;
   }
+  Act act16(int H, int W, int C) {
+    Act a = act(H, W, C);
+    if (c.opt_raw16) a.raw16 = half2(a.count(), true);
+    return a;
+  }
+  ActOp raw16_operand(const Act& x) {
+    ActOp a;
+    a.n = nb, a.H = x.H, a.W = x.W, a.C = x.C, a.p = x.raw16;
+    return a;
+  }
   Act act(int H, int W, int C) {
     Act a;
     a.n = nb, a.H = H, a.W = W, a.C = C;
@@ -256,14 +268,13 @@ struct Fwd {
     a.n = nb, a.H = x0.H, a.W = x0.W, a.C = C;
     a.p = half2((size_t)nb * x0.H * x0.W * C, lo);
     SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
-    double* sums = gn_sums + (size_t)gn_slot * nb * 64;
     unsigned int* tk = gn_tickets + (size_t)gn_slot * nb * 2;
     gn_slot++;
     const int HW = x0.H * x0.W;
     float* part = c.work.get<float>(gn_fused_partial_floats(nb, HW));
     KernelScope ks(c, KC_PREP, 0, (double)nb * HW * C * (8.0 + 2.0 + (lo ? 2.0 : 0.0)));
     gn_fused_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, nw.eps,
-                    a.p, sums, part, tk, tk + nb, c.stream);
+                    a.p, part, tk, c.stream);
     return a;
   }
   // raw (un-normalised) fp16 staging; mode 0, PREP_PHASE2 (stride-2 conv input)
@@ -295,8 +306,16 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
   const size_t mark = c.work.off;
   const bool lo = passes >= 2 || c.opt_precision >= 2;
   ActOp a = f.gn_operand(x0, x1, n1, true, lo);
-  ActOp raw;
-  if (skip) raw = f.raw_operand(x0, x1, 0, lo);
+  ActOp raw, raw1;
+  const bool have16 = x0.raw16.hi && (!lo || x0.raw16.lo) && (!x1 || (x1->raw16.hi && (!lo || x1->raw16.lo)));
+  if (skip) {
+    if (have16) {
+      raw = f.raw16_operand(x0);
+      if (x1) raw1 = f.raw16_operand(*x1);
+    } else {
+      raw = f.raw_operand(x0, x1, 0, lo);
+    }
+  }
   Act h = f.act(x0.H, x0.W, c1.cout);
   {
     Epilogue ep;
@@ -309,11 +328,11 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
     Epilogue ep;
     ep.out_f32 = out.p;
     ep.bias = skip->bias;
-    run_gemm(c, G_CONV1, raw, nullptr, skip->packed, passes, ep);
+    run_gemm(c, G_CONV1, raw, (have16 && x1) ? &raw1 : nullptr, skip->packed, passes, ep);
   }
   {
     Epilogue ep;
-    ep.out_f32 = out.p;
+    ep.out_f32 = out.p, ep.out_f16 = out.raw16;
     ep.bias = c2.bias;
     ep.residual = skip ? out.p : x0.p;  // in-place accumulate onto the skip-conv result, or + x
     run_gemm(c, G_CONV3, b, nullptr, c2.packed, passes, ep);
@@ -430,7 +449,7 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   // ---- proj_out + residual with the block input
   {
     Epilogue ep;
-    ep.out_f32 = out.p, ep.residual = x.p, ep.bias = s.proj_out.bias;
+    ep.out_f32 = out.p, ep.out_f16 = out.raw16, ep.residual = x.p, ep.bias = s.proj_out.bias;
     run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.proj_out.packed, P, ep);
   }
   c.work.off = mark;
@@ -511,29 +530,30 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
     Act o;
     switch (b.kind) {
       case BK_CONV: {
-        o = f.act(H, W, b.cout);
+        o = f.act16(H, W, b.cout);
         KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 36.0 * b.cout);
-        conv3x3_cin4_launch(io.x, f.nb, H, W, mptr(c, b.conv.wi), b.conv.bias, b.cout, nullptr, nullptr, 1.f, o.p, c.stream);
+        conv3x3_cin4_launch(io.x, f.nb, H, W, mptr(c, b.conv.wi), b.conv.bias, b.cout, nullptr, nullptr, 1.f, o.p, o.raw16,
+                            c.stream);
         break;
       }
       case BK_DOWN: {  // unet/mod.rs:412-427: 3x3 stride 2 pad 1
-        o = f.act(H / 2, W / 2, b.cout);
+        o = f.act16(H / 2, W / 2, b.cout);
         const size_t mk = c.work.off;
         const bool lo = b.conv.passes >= 2 || c.opt_precision >= 2;
         ActOp a = f.raw_operand(x0, nullptr, PREP_PHASE2, lo);
         Epilogue ep;
-        ep.out_f32 = o.p, ep.bias = b.conv.bias;
+        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias;
         run_gemm(c, G_CONV3_S2, a, nullptr, b.conv.packed, b.conv.passes, ep);
         c.work.off = mk;
         H /= 2, W /= 2;
         break;
       }
       case BK_R:
-        o = f.act(H, W, b.cout);
+        o = f.act16(H, W, b.cout);
         do_res(b.res, x0, x1, o);
         break;
       case BK_RT: {
-        o = f.act(H, W, b.cout);
+        o = f.act16(H, W, b.cout);
         Act r = f.act(H, W, b.cout);
         do_res(b.res, x0, x1, r);
         run_spatial_transformer(f, b.st, cs, cs.kv[st_index++], r, o);
@@ -541,20 +561,21 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
       }
       case BK_RU:
       case BK_RTU: {
-        o = f.act(2 * H, 2 * W, b.cout);
+        o = f.act16(2 * H, 2 * W, b.cout);
         const size_t mk = c.work.off;
-        Act r = f.act(H, W, b.cout);
+        // the tensor the upsample conv reads (resblock or transformer output) gets its fp16 copy from its producer
+        Act r = b.kind == BK_RTU ? f.act(H, W, b.cout) : f.act16(H, W, b.cout);
         do_res(b.res, x0, x1, r);
         Act u = r;
         if (b.kind == BK_RTU) {
-          u = f.act(H, W, b.cout);
+          u = f.act16(H, W, b.cout);
           run_spatial_transformer(f, b.st, cs, cs.kv[st_index++], r, u);
         }
         // unet/mod.rs:390-398: nearest 2x + conv3x3, folded into four 2x2-tap phase convolutions
         const bool lo = b.conv.passes >= 2 || c.opt_precision >= 2;
-        ActOp a = f.raw_operand(u, nullptr, 0, lo);
+        ActOp a = u.raw16.hi ? f.raw16_operand(u) : f.raw_operand(u, nullptr, 0, lo);
         Epilogue ep;
-        ep.out_f32 = o.p, ep.bias = b.conv.bias;
+        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias;
         run_gemm(c, G_CONV3_UP2, a, nullptr, b.conv.packed, b.conv.passes, ep);
         // `o` was allocated before mk, so releasing the temporaries keeps it alive
         c.work.off = mk;
@@ -571,7 +592,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   }
   // middle block (:130)
   {
-    Act r1 = f.act(H, W, 1280), t = f.act(H, W, 1280), r2 = f.act(H, W, 1280);
+    Act r1 = f.act(H, W, 1280), t = f.act(H, W, 1280), r2 = f.act16(H, W, 1280);
     do_res(m.mid_res1, x, nullptr, r1);
     run_spatial_transformer(f, m.mid_st, cs, cs.kv[st_index++], r1, t);
     do_res(m.mid_res2, t, nullptr, r2);
@@ -674,7 +695,7 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   {
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 36.0 * 512);
     conv3x3_cin4_launch(d_latent, f.nb, H, W, mptr(c, m.vae_conv_in.wi), m.vae_conv_in.bias, 512, mptr(c, m.post_quant.wi),
-                        m.post_quant.bias, pre_scale, x.p, c.stream);
+                        m.post_quant.bias, pre_scale, x.p, Half2Ptr{}, c.stream);
   }
   // Mid (autoencoder/mod.rs:456-463)
   {
@@ -688,17 +709,18 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   for (int i = 0; i < 4; ++i) {
     DecoderBlockW& db = m.dec[i];
     for (int j = 0; j < 3; ++j) {
-      Act o = f.act(H, W, db.res[j].cout);
+      // the tensor the upsampler reads gets its fp16 hi/lo copy from the producing epilogue
+      Act o = (j == 2 && db.has_up) ? f.act16(H, W, db.res[j].cout) : f.act(H, W, db.res[j].cout);
       run_resnet(f, db.res[j], x, o);
       x = o;
     }
     if (db.has_up) {
-      Act o = f.act(2 * H, 2 * W, db.up.cout);
+      Act o = f.act16(2 * H, 2 * W, db.up.cout);  // read raw by the next block's nin_shortcut
       const size_t mk = c.work.off;
       const bool lo = db.up.passes >= 2 || c.opt_precision >= 2;
-      ActOp a = f.raw_operand(x, nullptr, 0, lo);
+      ActOp a = x.raw16.hi ? f.raw16_operand(x) : f.raw_operand(x, nullptr, 0, lo);
       Epilogue ep;
-      ep.out_f32 = o.p, ep.bias = db.up.bias;
+      ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = db.up.bias;
       run_gemm(c, G_CONV3_UP2, a, nullptr, db.up.packed, db.up.passes, ep);
       c.work.off = mk;
       x = o;

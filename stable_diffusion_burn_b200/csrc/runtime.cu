@@ -1,6 +1,8 @@
 // runtime.cu — context plumbing, TMA tensor maps and the GEMM op builder.
 #include "runtime.cuh"
 
+#include <algorithm>
+
 #include <cudaTypedefs.h>
 
 #include <cmath>
@@ -9,6 +11,7 @@
 
 namespace sdb {
 
+int g_pdl_late = 0;  // SDB_PDL=2: GEMMs release their dependents at epilogue start instead of at entry
 bool g_pdl_enabled = false;  // measured: PDL is ~3 % slower here (early CTAs compete with the draining kernel); SDB_PDL=1 enables it
 
 // ------------------------------------------------------------------ arena
@@ -285,7 +288,8 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     split = (iters + per - 1) / per;
   }
   p.split_k = split;
-  if (c.debug_sync || c.profiling) {
+  static const bool gemm_dbg = getenv("SDB_GEMM_DBG") != nullptr;
+  if (c.debug_sync || c.profiling || gemm_dbg) {
     char buf[256];
     snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d cluster=%d",
              kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW, p.cluster);
@@ -300,11 +304,19 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.residual = ep.residual;
   p.geglu = ep.geglu;
   p.act = ep.act;
+  p.pdl_late = g_pdl_late;
+  {
+    static const int dbg_mode = getenv("SDB_GEMM_DBG_MODE") ? atoi(getenv("SDB_GEMM_DBG_MODE")) : 0;
+    p.dbg_mode = dbg_mode;
+  }
   const int nout = ep.geglu ? w.N / 2 : w.N;
   p.ldc = ep.ldc ? ep.ldc : nout;
   p.ldc16 = ep.ldc16 ? ep.ldc16 : nout;
+  SDB_CHECK(!(ep.rowbias && ep.residual), "epilogue takes a time-embedding row or a residual, not both");
   p.os = (kind == G_CONV3_UP2) ? 2 : 1;
   p.OH = a0.H * p.os, p.OW = a0.W * p.os;
+  SDB_CHECK((double)a0.n * p.OH * p.OW * (double)std::max(p.ldc, p.ldc16) < 2147483648.0,
+            "GEMM output exceeds 2^31 elements (the epilogue uses 32-bit element offsets)");
 
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -353,8 +365,26 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       // flops = algorithmic 2*M*N*K of this launch; the class' second counter holds the ISSUED tensor-core
       // FLOPs (x passes for split-fp16 products), not bytes
       (void)bytes;
-      KernelScope ks(c, KC_GEMM, flops, flops * passes);
-      gemm_tc_launch(maps, p, BN, passes, c.stream);
+      static const bool dbg_on = getenv("SDB_GEMM_DBG") != nullptr;
+      static long long* dbg_buf = nullptr;
+      if (dbg_on) {
+        if (!dbg_buf) SDB_CUDA(cudaMallocManaged(&dbg_buf, 16 * sizeof(long long)));
+        SDB_CUDA(cudaStreamSynchronize(c.stream));
+        memset(dbg_buf, 0, 16 * sizeof(long long));
+        p.dbg = dbg_buf;
+      }
+      const std::string label = c.dbg_label;
+      {
+        KernelScope ks(c, KC_GEMM, flops, flops * passes);
+        gemm_tc_launch(maps, p, BN, passes, c.stream);
+      }
+      if (dbg_on) {  // bring-up aid: cycle stamps of CTA (0,0,0), printed relative to kernel entry
+        SDB_CUDA(cudaStreamSynchronize(c.stream));
+        fprintf(stderr, "gemm_dbg %s | cycles since entry: prologue %lld tma0 %lld landed %lld lastmma %lld accum %lld epi %lld exit %lld | chunk0: ld %lld stage %lld finish %lld (bias %lld loads0 %lld batch0 %lld)\n",
+                label.c_str(), dbg_buf[1] - dbg_buf[0], dbg_buf[2] - dbg_buf[0], dbg_buf[3] - dbg_buf[0],
+                dbg_buf[4] - dbg_buf[0], dbg_buf[5] - dbg_buf[0], dbg_buf[6] - dbg_buf[0], dbg_buf[7] - dbg_buf[0], dbg_buf[9] - dbg_buf[8], dbg_buf[10] - dbg_buf[9],
+                dbg_buf[11] - dbg_buf[10], dbg_buf[12] - dbg_buf[10], dbg_buf[13] - dbg_buf[12], dbg_buf[14] - dbg_buf[13]);
+      }
     }
     // (the split-K reduction happens inside the kernel: the last CTA of a tile folds the partials)
   }
