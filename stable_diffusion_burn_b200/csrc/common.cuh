@@ -53,8 +53,16 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 // PDL device side: let the next kernel of the stream start launching, then wait until everything the
 // previous kernel wrote is visible. Harmless when the launch carried no PDL attribute.
+#ifdef SDB_PDL_WAIT_FIRST  // experiment: depth-1 cascade (a kernel releases its dependents only once its own inputs are complete)
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
   pdl_wait();

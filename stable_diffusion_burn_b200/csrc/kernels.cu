@@ -329,9 +329,10 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
   }
 }
 
+int g_gn_min_pix = 1;  // pixels per CTA floor: small feature maps are latency-bound, so they get many small CTAs
 static int gn_fused_pix(int n, int HW) {
   int pix = (int)((((long long)HW * n) + 295) / 296);  // <= 296 CTAs (2 per SM): short fold, always co-resident
-  return pix < 8 ? 8 : pix;
+  return pix < g_gn_min_pix ? g_gn_min_pix : pix;
 }
 size_t gn_fused_partial_floats(int n, int HW) { return (size_t)n * ceil_div(HW, gn_fused_pix(n, HW)) * 64; }
 
