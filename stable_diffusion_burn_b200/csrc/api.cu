@@ -270,6 +270,8 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_pair_bn256 = value;
   else if (k == "raw16")
     c.opt_raw16 = value;
+  else if (k == "skip_merge")
+    c.opt_skip_merge = value;
   else if (k == "gn_min_pix")
     g_gn_min_pix = value < 1 ? 1 : value;
   else

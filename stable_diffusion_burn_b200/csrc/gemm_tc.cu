@@ -87,7 +87,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
   const int col0 = blockIdx.y * BN;
 
-  const int total_iters = p.num_taps * p.kc;
+  const int main_iters = p.num_taps * p.kc;
+  const int total_iters = main_iters + p.xkc;
   const int per_split = (total_iters + p.split_k - 1) / p.split_k;
   const int it_begin = blockIdx.z * per_split;
   const int it_end = min(total_iters, it_begin + per_split);
@@ -136,24 +137,36 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (leader) mbar_expect_tx(&full_bar[s], L::BYTES * CG);  // both CTAs' loads report to the leader's barrier
         uint8_t* st = smem + s * L::BYTES;
-        const int tap = it / p.kc;
-        const int cc = it - tap * p.kc;
-        const int src = cc >= p.kc0 ? 1 : 0;
-        const int c0 = (cc - (src ? p.kc0 : 0)) * BK;
-        const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
+        // iteration -> (activation source, channel chunk, tap shift) and the weight map / K coordinate that go with it
+        int src, c0, cw, ch, cp, bk;
+        const CUtensorMap* bm;
+        if (it < main_iters) {
+          const int tap = it / p.kc;
+          const int cc = it - tap * p.kc;
+          src = cc >= p.kc0 ? 1 : 0;
+          c0 = (cc - (src ? p.kc0 : 0)) * BK;
+          cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
+          bm = maps.b, bk = it * BK;
+        } else {
+          const int e = it - main_iters;
+          src = e >= p.xkc0 ? 3 : 2;
+          c0 = (e - (src == 3 ? p.xkc0 : 0)) * BK;
+          cw = w0, ch = h0, cp = 0;
+          bm = maps.bx, bk = e * BK;
+        }
         uint8_t* sb = st + L::A_TILES * A_TILE_BYTES;
         if (!TWO) {
           tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
           if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
-          tma_load_2d(sb, &maps.b[0], &full_bar[s], it * BK, col0);
-          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &maps.b[1], &full_bar[s], it * BK, col0);
+          tma_load_2d(sb, &bm[0], &full_bar[s], bk, col0);
+          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &bm[1], &full_bar[s], bk, col0);
         } else {
           // own 128 A rows + rows [crank*BN/2, +BN/2) of the weight tile, into this CTA's smem
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
           tma_load_5d_2sm(st, &maps.a[src][0], fb, c0, cw, ch, cp, n0);
           if (PASSES >= 2) tma_load_5d_2sm(st + A_TILE_BYTES, &maps.a[src][1], fb, c0, cw, ch, cp, n0);
-          tma_load_2d_2sm(sb, &maps.b[0], fb, it * BK, col0 + crank * (BN / 2));
-          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &maps.b[1], fb, it * BK, col0 + crank * (BN / 2));
+          tma_load_2d_2sm(sb, &bm[0], fb, bk, col0 + crank * (BN / 2));
+          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &bm[1], fb, bk, col0 + crank * (BN / 2));
         }
         if (dbg && it == it_begin) dbg[2] = clock64();
         if (++s == STAGES) {

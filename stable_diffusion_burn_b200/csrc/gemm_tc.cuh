@@ -9,7 +9,9 @@ namespace sdb {
 // B operand = packed fp16 weights [N][K] (K-major), K index = tap * Cin_total + c.
 // D (fp32, TMEM) [128 rows = TN*TH*TW output pixels][BN output channels].
 struct GemmMaps {
-  CUtensorMap a[2][2];  // [source 0/1][hi/lo]
+  CUtensorMap a[4][2];  // [source][hi/lo]: 0/1 = channel-concatenated operands of every tap; 2/3 = "extra K" operands read at
+                        // the centre tap only, appended after the taps (the ResBlock's 1x1 skip conv folded into conv_out)
+  CUtensorMap bx[2];    // weights of the extra-K segment [N][xK]
   CUtensorMap b[2];     // [hi/lo]  box {64, BN} (cluster = 1) or {64, BN/2} (cluster = 2: each CTA of a pair
                         //          stages the half of the weight tile that the cta_group::2 MMA reads from it)
 };
@@ -22,6 +24,7 @@ struct GemmParams {
   int kc;              // 64-wide channel chunks per tap (both sources)
   int kc0;             // chunks taken from source 0
   int num_taps;
+  int xkc, xkc0;       // extra-K chunks appended after the taps (total, and those from source 2)
   int8_t tap_dh[9], tap_dw[9], tap_ph[9];
   int split_k;
   int cluster;             // 1, or 2 = CTA pairs along M issue tcgen05.mma.cta_group::2 (256 x BN)

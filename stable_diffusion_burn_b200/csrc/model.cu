@@ -81,7 +81,11 @@ static void pack_resblock(Ctx& c, ResBlockW& r, int passes) {
   r.passes = passes;
   pack_norm(c, r.norm_in), pack_norm(c, r.norm_out);
   pack_conv(c, r.conv_in), pack_conv(c, r.conv_out);
-  if (r.has_skip) pack_conv(c, r.skip);
+  if (r.has_skip) {
+    pack_conv(c, r.skip);
+    r.bias_merged = c.packed.get<float>(r.cout);
+    add_vec_launch(r.conv_out.bias, r.skip.bias, r.cout, r.bias_merged, c.stream);
+  }
   r.lin_embed.bias = mptr(c, r.lin_embed.bi);
 }
 static void pack_st(Ctx& c, SpatialTransformerW& s, int passes) {
@@ -109,7 +113,11 @@ static void pack_resnet(Ctx& c, ResnetW& r, int passes) {
   r.passes = passes;
   pack_norm(c, r.norm1), pack_norm(c, r.norm2);
   pack_conv(c, r.conv1), pack_conv(c, r.conv2);
-  if (r.has_nin) pack_conv(c, r.nin);
+  if (r.has_nin) {
+    pack_conv(c, r.nin);
+    r.bias_merged = c.packed.get<float>(r.cout);
+    add_vec_launch(r.conv2.bias, r.nin.bias, r.cout, r.bias_merged, c.stream);
+  }
 }
 
 void model_finalize(Ctx& c) {
@@ -301,7 +309,7 @@ struct Fwd {
 
 // reference unet/mod.rs:712-734 (emb_bias = conv_in.bias + lin_embed(silu(emb)); nullptr for the VAE ResnetBlock)
 static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& n2, const ConvW& c2, const ConvW* skip,
-                         int passes, const Act& x0, const Act* x1, const float* emb_bias, Act& out) {
+                         const float* bias_merged, int passes, const Act& x0, const Act* x1, const float* emb_bias, Act& out) {
   Ctx& c = f.c;
   const size_t mark = c.work.off;
   const bool lo = passes >= 2 || c.opt_precision >= 2;
@@ -324,7 +332,9 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
     run_gemm(c, G_CONV3, a, nullptr, c1.packed, passes, ep);
   }
   ActOp b = f.gn_operand(h, nullptr, n2, true, lo);
-  if (skip) {
+  // the 1x1 skip conv rides in conv_out's K loop when its inputs already exist as fp16 operands
+  const bool merge = skip && have16 && bias_merged && c.opt_skip_merge;
+  if (skip && !merge) {
     Epilogue ep;
     ep.out_f32 = out.p;
     ep.bias = skip->bias;
@@ -333,9 +343,16 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
   {
     Epilogue ep;
     ep.out_f32 = out.p, ep.out_f16 = out.raw16;
-    ep.bias = c2.bias;
-    ep.residual = skip ? out.p : x0.p;  // in-place accumulate onto the skip-conv result, or + x
-    run_gemm(c, G_CONV3, b, nullptr, c2.packed, passes, ep);
+    ExtraK xk;
+    if (merge) {
+      xk.x0 = raw, xk.has_x1 = x1 != nullptr, xk.w = skip->packed;
+      if (x1) xk.x1 = raw1;
+      ep.bias = bias_merged;
+    } else {
+      ep.bias = c2.bias;
+      ep.residual = skip ? out.p : x0.p;  // in-place accumulate onto the skip-conv result, or + x
+    }
+    run_gemm(c, G_CONV3, b, nullptr, c2.packed, passes, ep, merge ? &xk : nullptr);
   }
   c.work.off = mark;  // temporaries are dead once the block's kernels are queued (stream order)
 }
@@ -523,7 +540,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   Act x;
   int H = io.H, W = io.W;
   auto do_res = [&](ResBlockW& r, const Act& x0, const Act* x1, Act& o) {
-    run_resblock(f, r.norm_in, r.conv_in, r.norm_out, r.conv_out, r.has_skip ? &r.skip : nullptr, r.passes, x0, x1,
+    run_resblock(f, r.norm_in, r.conv_in, r.norm_out, r.conv_out, r.has_skip ? &r.skip : nullptr, r.bias_merged, r.passes, x0, x1,
                  emb_rows + r.emb_off, o);
   };
   auto do_block = [&](UNetBlockW& b, const Act& x0, const Act* x1) -> Act {
@@ -616,7 +633,8 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
 
 // ================================================================================ VAE decoder
 static void run_resnet(Fwd& f, ResnetW& r, const Act& x, Act& out) {
-  run_resblock(f, r.norm1, r.conv1, r.norm2, r.conv2, r.has_nin ? &r.nin : nullptr, r.passes, x, nullptr, nullptr, out);
+  run_resblock(f, r.norm1, r.conv1, r.norm2, r.conv2, r.has_nin ? &r.nin : nullptr, r.bias_merged, r.passes, x, nullptr, nullptr,
+               out);
 }
 
 // reference autoencoder/mod.rs:562-608: 1 head, d = C = 512, N = H*W tokens. S is materialised per image

@@ -35,6 +35,7 @@ struct ResBlockW {
   ConvW conv_in, conv_out, skip;
   LinW lin_embed;
   bool has_skip = false;
+  float* bias_merged = nullptr;  // conv_out.bias + skip_connection.bias (skip conv folded into conv_out's K loop)
   int emb_off = 0;  // offset of this block's row in the fused time-embedding GEMV output
   int passes = 1;
 };
@@ -71,6 +72,7 @@ struct ResnetW {
   NormW norm1, norm2;
   ConvW conv1, conv2, nin;
   bool has_nin = false;
+  float* bias_merged = nullptr;  // conv2.bias + nin_shortcut.bias
   int passes = 1;
 };
 struct VaeAttnW {

@@ -190,7 +190,8 @@ static int pow2_ceil(int x) {
 }
 
 // ------------------------------------------------------------------ GEMM op
-void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const WeightOp& w, int passes, const Epilogue& ep) {
+void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const WeightOp& w, int passes, const Epilogue& ep,
+              const ExtraK* xk) {
   ActOp a0 = a0in, a1;
   if (a1in) a1 = *a1in;
   if (kind == G_CONV1) {  // a 1x1 conv over NHWC is a plain row-major GEMM
@@ -240,6 +241,16 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       throw Error("bad gemm kind");
   }
   SDB_CHECK(w.K == p.num_taps * Ctot, "weight K does not match the operand");
+  if (xk) {
+    const int xC = xk->x0.C + (xk->has_x1 ? xk->x1.C : 0);
+    SDB_CHECK(kind == G_CONV3 || kind == G_LINEAR, "extra-K operands need an unshifted output grid");
+    SDB_CHECK(xk->x0.n == a0.n && xk->x0.H == a0.H && xk->x0.W == a0.W && xk->x0.P == 1 && xk->x0.C % 64 == 0, "extra-K geometry");
+    SDB_CHECK(!xk->has_x1 || (xk->x1.n == a0.n && xk->x1.H == a0.H && xk->x1.W == a0.W && xk->x1.C % 64 == 0), "extra-K geometry");
+    SDB_CHECK(xk->w.N == w.N && xk->w.K == xC, "extra-K weights");
+    SDB_CHECK(passes < 2 || (xk->x0.p.lo && (!xk->has_x1 || xk->x1.p.lo)), "multi-pass GEMM needs the lo half of the extra operands");
+    SDB_CHECK(passes < 3 || xk->w.p.lo, "3-pass GEMM needs the lo half of the extra weights");
+    p.xkc0 = xk->x0.C / 64, p.xkc = xC / 64;
+  }
 
   // M tile = TN x TH x TW output pixels
   p.TW = std::min(pow2_floor(a0.W), 128);
@@ -271,7 +282,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
 
 
   // split-K when the grid cannot fill the machine and the K loop is long
-  const int iters = p.num_taps * p.kc;
+  const int iters = p.num_taps * p.kc + p.xkc;
   int split = 1;
   if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
     const int ctas = m_tiles * n_tiles;
@@ -332,8 +343,18 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     if (passes >= 2) maps.a[1][1] = make_act_map(a1.p.lo, a1.C, a1.W, a1.H, a1.P, a1.n, p.TW, p.TH, p.TN);
   }
 
+  for (int sidx = 2; sidx < 4; ++sidx) maps.a[sidx][0] = maps.a[sidx][1] = maps.a[0][0];
+  if (xk) {
+    auto xmaps = [&](const ActOp& x, int sidx) {
+      maps.a[sidx][0] = make_act_map(x.p.hi, x.C, x.W, x.H, x.P, x.n, p.TW, p.TH, p.TN);
+      maps.a[sidx][1] = passes >= 2 ? make_act_map(x.p.lo, x.C, x.W, x.H, x.P, x.n, p.TW, p.TH, p.TN) : maps.a[sidx][0];
+    };
+    xmaps(xk->x0, 2);
+    if (xk->has_x1) xmaps(xk->x1, 3);
+  }
+
   const double Mtot = (double)a0.n * a0.H * a0.W;
-  const double flops = 2.0 * Mtot * (double)w.N * (double)w.K;  // algorithmic (one product per MAC)
+  const double flops = 2.0 * Mtot * (double)w.N * ((double)w.K + 64.0 * p.xkc);  // algorithmic (one product per MAC)
   const double bytes = Mtot * Ctot * 2.0 + (double)w.N * w.K * 2.0 + Mtot * nout * 4.0;
 
   for (int phase = 0; phase < phases_out; ++phase) {
@@ -344,6 +365,12 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     maps.b[0] = make_w_map(whi, w.K, wrows, bbox, w.ld);
     maps.b[1] = maps.b[0];
     if (passes >= 3) maps.b[1] = make_w_map(wlo, w.K, wrows, bbox, w.ld);
+    maps.bx[0] = maps.bx[1] = maps.b[0];
+    if (xk) {
+      const int xrows = xk->w.rows ? xk->w.rows : xk->w.N;
+      maps.bx[0] = make_w_map(xk->w.p.hi, xk->w.K, xrows, bbox, xk->w.ld);
+      maps.bx[1] = passes >= 3 ? make_w_map(xk->w.p.lo, xk->w.K, xrows, bbox, xk->w.ld) : maps.bx[0];
+    }
     if (kind == G_CONV3_UP2) {
       const int a = phase >> 1, b = phase & 1;
       p.oa = a, p.ob = b;

@@ -106,6 +106,7 @@ struct Ctx {
   int opt_graphs = 1;
   int opt_splitk = 1;
   int opt_pair_bn256 = 0;
+  int opt_skip_merge = 1; // ResBlock skip 1x1 conv folded into conv_out's K loop (needs raw16)
   int opt_raw16 = 1;      // epilogues also write the fp16 hi/lo copy a later raw-operand consumer needs (no staging launch)
   int opt_cluster = 1;    // CTA pairs issue cta_group::2 MMAs (256 x BN) wherever the M-tile count is even and K is not split
   // profiling
@@ -135,9 +136,18 @@ struct KernelScope {  // RAII: counts a launch, optionally brackets it with even
 };
 void profile_collect(Ctx& c);
 
+// "extra K": operands read at the centre tap only, appended to a conv's K loop — the ResBlock's 1x1 skip conv
+// (unet/mod.rs:729-731) folded into conv_out, so the block needs neither a separate launch nor a residual read
+struct ExtraK {
+  ActOp x0, x1;
+  bool has_x1 = false;
+  WeightOp w;  // [N][x0.C + x1.C]
+};
+
 // one tcgen05 GEMM / implicit conv (+ split-K reduction when chosen)
 //   a0 (+a1 = channel concat), geometry kind, weights, passes (1..3), epilogue
-void run_gemm(Ctx& c, int kind, const ActOp& a0, const ActOp* a1, const WeightOp& w, int passes, const Epilogue& ep);
+void run_gemm(Ctx& c, int kind, const ActOp& a0, const ActOp* a1, const WeightOp& w, int passes, const Epilogue& ep,
+              const ExtraK* xk = nullptr);
 
 // fused attention over fp16 matrices:
 //   q  [nb*q_rows][ldq]  head h at columns q_col0 + h*dpad (zero padded to dpad)
