@@ -270,6 +270,10 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_pair_bn256 = value;
   else if (k == "raw16")
     c.opt_raw16 = value;
+  else if (k == "splitk_min_iters")
+    c.opt_splitk_min_iters = value;
+  else if (k == "splitk_chunk")
+    c.opt_splitk_chunk = value < 1 ? 1 : value;
   else if (k == "skip_merge")
     c.opt_skip_merge = value;
   else if (k == "gn_min_pix")

@@ -286,10 +286,10 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   int split = 1;
   if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
     const int ctas = m_tiles * n_tiles;
-    if (ctas <= 74 && iters >= 32) {
+    if (ctas <= 74 && iters >= c.opt_splitk_min_iters) {
       // floor: ctas*split must stay within ONE wave of the 148 SMs (a 2-wave grid costs 2x, see profiles/r1);
       // every split keeps >= 16 k-chunks so the rendezvous + fold stays small against its mainloop
-      split = std::min(std::min(148 / ctas, iters / 16), 16);
+      split = std::min(std::min(148 / ctas, iters / c.opt_splitk_chunk), 16);
       if (split < 1) split = 1;
     }
   }
