@@ -48,11 +48,23 @@ def _enter(block):
     _EMU["cur"] = block
 
 
+def set_emulation_policy(policy):
+    """Per-block override: {block tap name: roles string}; blocks not listed use the global roles. Roles: 'a'/'w' Linear
+    activations/weights, 'A'/'W' conv activations/weights, 'q' attention matmul operands."""
+    _EMU["policy"] = policy
+
+
 def _q(x, role="a"):
     m = _EMU["mode"]
-    if m is None or role not in _EMU["roles"]:
+    pol = _EMU.get("policy")
+    roles = _EMU["roles"]
+    if pol is not None and _EMU["cur"] in pol:
+        roles = pol[_EMU["cur"]]
+    elif _EMU["blocks"] is not None and _EMU["cur"] not in _EMU["blocks"]:
         return x
-    if _EMU["blocks"] is not None and _EMU["cur"] not in _EMU["blocks"]:
+    if not any(ch.isupper() for ch in roles):
+        roles = roles + roles.upper()  # "awq" (no conv-specific letters) covers the conv operands too
+    if m is None or role not in roles:
         return x
     if m == "fp16":
         return x.to(torch.float16).to(x.dtype)
@@ -92,7 +104,7 @@ def linear(P, name, x):
 def conv2d(P, name, x, stride=1, padding=0):
     """burn nn::conv::Conv2d -> at::conv2d, OIHW (reference src/model/load.rs:118-160)."""
     b = P(f"{name}/bias") if P.has(f"{name}/bias") else None
-    return F.conv2d(_q(x, "a"), _q(P(f"{name}/weight"), "w"), b, stride=stride, padding=padding)
+    return F.conv2d(_q(x, "A"), _q(P(f"{name}/weight"), "W"), b, stride=stride, padding=padding)
 
 
 def silu(x):

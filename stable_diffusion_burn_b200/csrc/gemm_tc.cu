@@ -55,15 +55,25 @@ __device__ __noinline__ void epilogue_store(float4 f, unsigned int o32, unsigned
 // Variants whose pipeline fits twice in an SM's shared memory are launched two CTAs per SM (<= 102 registers per thread);
 // the others own the SM and may use the whole register file.
 template <int BN, int PASSES, int STAGES, int CG>
-constexpr int min_ctas_per_sm() {
+__host__ __device__ constexpr int min_ctas_per_sm() {
   return STAGES * StageLayout<BN, PASSES, CG>::BYTES <= 108 * 1024 ? 2 : 1;
 }
 
+// Epilogue warps (a multiple of 4: one group per TMEM lane quarter). Measured: 16 warps on the SM-owning variants do not
+// shorten the epilogue (6.4k vs 6.7k cycles for 128 x 160) and lengthen the tail, so every variant uses 8.
 template <int BN, int PASSES, int STAGES, int CG>
-__global__ void __launch_bounds__(320, min_ctas_per_sm<BN, PASSES, STAGES, CG>())
+__host__ __device__ constexpr int epilogue_warps() {
+  return 8;
+}
+
+template <int BN, int PASSES, int STAGES, int CG>
+__global__ void __launch_bounds__(64 + 32 * epilogue_warps<BN, PASSES, STAGES, CG>(), min_ctas_per_sm<BN, PASSES, STAGES, CG>())
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using L = StageLayout<BN, PASSES, CG>;
   constexpr bool TWO = CG == 2;
+  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();  // epilogue warps
+  constexpr int EG = EW / 4;                                    // warps sharing one TMEM lane quarter
+  constexpr int CSTEP = 32 * EG;                                // column stride between the chunks of one warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -228,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     // are idle by now; rows padded to 144 B keep both the 128-bit writes and reads bank-conflict free) and
     // written/read as 4 rows x 128 contiguous bytes per warp instruction.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which half of the column chunks this warp owns
+    const int half = (warp - 2) >> 2;   // which share of the column chunks this warp owns (0..EG-1)
     const int r = q * 32 + lane;        // accumulator row
     const int pw = w0 + r % p.TW;
     const int phh = h0 + (r / p.TW) % p.TH;
@@ -243,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     // (~650 cycles each, measured with clock64 stamps): everything issued here is off that chain.
     const int sub = lane >> 3;          // row within a group of 4
     const int cq = (lane & 7) * 4;      // 4-column group inside the 32-column chunk
-    constexpr int NCHUNK = (BN + 63) / 64;
+    constexpr int NCHUNK = (BN + CSTEP - 1) / CSTEP;
     int mr8[8], ao[8];
     float4 bvs[NCHUNK], ad[8];
     const float* ad_ptr = p.residual ? p.residual : p.rowbias;
@@ -261,9 +271,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
 #pragma unroll
       for (int j = 0; j < NCHUNK; ++j) {
-        const int col = col0 + half * 32 + j * 64 + cq;
+        const int col = col0 + half * 32 + j * CSTEP + cq;
         bvs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (plain && p.bias && half * 32 + j * 64 < BN && col < p.N) bvs[j] = *reinterpret_cast<const float4*>(p.bias + col);
+        if (plain && p.bias && half * 32 + j * CSTEP < BN && col < p.N) bvs[j] = *reinterpret_cast<const float4*>(p.bias + col);
       }
     }
     auto issue_addends = [&](int col) {
@@ -283,8 +293,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
     constexpr uint32_t TROW = 144;                                   // padded row pitch of the staging tile (bytes)
-    const uint32_t tile_s = smem_u32(smem) + (warp - 2) * (32 * TROW);  // one 32-row tile per warp (36.9 KB in all)
-    const uint32_t tile2_s = tile_s + 8 * 32 * TROW;                     // second bank, GEGLU only (x | gate)
+    const uint32_t tile_s = smem_u32(smem) + (warp - 2) * (32 * TROW);  // one 32-row tile per warp (4.6 KB each)
+    const uint32_t tile2_s = tile_s + EW * 32 * TROW;                    // second bank, GEGLU only (x | gate)
 
     auto stage = [&](uint32_t t, const uint32_t (&v)[32]) {
 #pragma unroll
@@ -311,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       const size_t Mtot = (size_t)p.nimg * p.OH * p.OW;
       float* wsbase = p.ws + (size_t)blockIdx.z * Mtot * p.N;
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
+      for (int c = half * 32; c < BN; c += CSTEP) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
@@ -327,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         __syncwarp();
       }
       __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have published their part of the tile
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");  // all epilogue warps have published their part of the tile
       // Tile-level rendezvous of the split_k CTAs (all co-resident: run_gemm keeps ctas*split within one wave), then
       // every CTA folds its own slice of the tile rows in z order (deterministic) and runs the epilogue on it.
       unsigned int* tk = p.tickets + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
@@ -340,14 +350,14 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
         __threadfence();
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       {
         const int rows_per = (BM + p.split_k - 1) / p.split_k;
         const int r0 = blockIdx.z * rows_per, r1 = min(BM, r0 + rows_per);
         constexpr int C4 = BN / 4;
         const int te = threadIdx.x - 64;
 #pragma unroll 1
-        for (int idx = te; idx < (r1 - r0) * C4; idx += 256) {
+        for (int idx = te; idx < (r1 - r0) * C4; idx += EW * 32) {
           const int rl = r0 + idx / C4;
           const int col = col0 + (idx % C4) * 4;
           const int qw = w0 + rl % p.TW, qh = h0 + (rl / p.TW) % p.TH, qn = n0 + rl / (p.TW * p.TH);
@@ -384,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (warp == 2 && lane == 0) {
         // last CTA to finish resets both counters: the buffer is all zero again for the next launch
         if (atomicAdd(tk + 1, 1u) == (unsigned)(p.split_k - 1)) {
@@ -397,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       constexpr int HB = BN / 2;
       const int ocol0 = blockIdx.y * HB;
 #pragma unroll 1
-      for (int c = half * 32; c < HB; c += 64) {
+      for (int c = half * 32; c < HB; c += CSTEP) {
         uint32_t v[32];
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
@@ -425,11 +435,11 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         __syncwarp();
       }
     } else {
-      constexpr int NCH = (BN + 63) / 64;  // column chunks per warp (the two warps of a lane quarter interleave them)
+      constexpr int NCH = NCHUNK;  // column chunks per warp (the warps of a lane quarter interleave them)
       if (!pre_issued) issue_addends(col0 + half * 32 + cq);
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        const int c = half * 32 + j * 64;
+        const int c = half * 32 + j * CSTEP;
         if (c < BN) {
           uint32_t v[32];
           tmem_ld32(trow + c, v);
@@ -461,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
           __syncwarp();
           // the next chunk's addends travel while its accumulator columns are read and staged
-          if (j + 1 < NCH && c + 64 < BN) issue_addends(col0 + c + 64 + cq);
+          if (j + 1 < NCH && c + CSTEP < BN) issue_addends(col0 + c + CSTEP + cq);
         }
       }
     }
@@ -502,7 +512,8 @@ constexpr int pick_stages_half() {
 template <int BN, int PASSES, int STAGES, int CG>
 static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem = STAGES * StageLayout<BN, PASSES, CG>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
-  static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 8 * 32 * 144, "epilogue staging tiles must fit in the stages");
+  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();
+  static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 2 * EW * 32 * 144, "epilogue staging tiles must fit in the stages");
   static bool attr_set = false;
   if (!attr_set) {
     SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -510,7 +521,7 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   }
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid, cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cfg.gridDim = grid, cfg.blockDim = dim3(64 + 32 * EW), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
