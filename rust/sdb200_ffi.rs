@@ -25,7 +25,9 @@ extern "C" {
     fn sdb_destroy(ctx: *mut SdbCtx) -> c_int;
     fn sdb_last_error(ctx: *mut SdbCtx) -> *const c_char;
     fn sdb_set_tensor(ctx: *mut SdbCtx, name: *const c_char, host: *const f32, dims: *const i64, ndim: c_int) -> c_int;
+    fn sdb_load_dump_dir(ctx: *mut SdbCtx, path: *const c_char) -> c_int;
     fn sdb_finalize_weights(ctx: *mut SdbCtx) -> c_int;
+    fn sdb_clip_forward(ctx: *mut SdbCtx, tokens: *const i32, n: c_int, l: c_int, out: *mut f32) -> c_int;
     fn sdb_unet_forward(ctx: *mut SdbCtx, x: *const f32, timestep: i32, context: *const f32, n: c_int, h: c_int,
                         w: c_int, l: c_int, out: *mut f32) -> c_int;
     fn sdb_decode_latent(ctx: *mut SdbCtx, latent: *const f32, n: c_int, h: c_int, w: c_int, img: *mut f32) -> c_int;
@@ -71,8 +73,21 @@ impl StableDiffusion {
         self.check(unsafe { sdb_set_tensor(self.ctx, cname.as_ptr(), data.as_ptr(), dims.as_ptr(), dims.len() as c_int) })
     }
 
+    /// Replaces `load_stable_diffusion(path, device)` (src/model/stablediffusion/load.rs:16-33): reads the dump-dir tree.
+    pub fn load_dump_dir(&self, path: &str) -> Result<(), SdbError> {
+        let cpath = CString::new(path).unwrap();
+        self.check(unsafe { sdb_load_dump_dir(self.ctx, cpath.as_ptr()) })
+    }
+
     pub fn finalize_weights(&self) -> Result<(), SdbError> {
         self.check(unsafe { sdb_finalize_weights(self.ctx) })
+    }
+
+    /// `CLIP::forward(tokens)` (src/model/clip/mod.rs:56-75): ids [n, l] (l <= 77, unpadded) -> [n, l, 768].
+    pub fn clip_forward(&self, tokens: &[i32], [n, l]: [usize; 2]) -> Result<Vec<f32>, SdbError> {
+        let mut out = vec![0f32; n * l * 768];
+        self.check(unsafe { sdb_clip_forward(self.ctx, tokens.as_ptr(), n as c_int, l as c_int, out.as_mut_ptr()) })?;
+        Ok(out)
     }
 
     /// `UNet::forward(x, timesteps, context)` (src/model/unet/mod.rs:109-114).

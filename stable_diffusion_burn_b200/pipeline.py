@@ -73,6 +73,12 @@ class StableDiffusion:
         self.ctx.finalize_weights()
         return self
 
+    def load_dump_dir(self, path: str):
+        """load_stable_diffusion(path, device) (src/model/stablediffusion/load.rs:16-33): the reference's dump-dir tree."""
+        self.ctx.load_dump_dir(path)
+        self.ctx.finalize_weights()
+        return self
+
     def load_arrays(self, arrays: dict):
         for name, a in arrays.items():
             self.ctx.set_tensor(name, a)
