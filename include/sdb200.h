@@ -101,6 +101,12 @@ int sdb_clip_forward(sdb_ctx* ctx, const int32_t* tokens, int n, int L, float* o
 /* device-pointer variant: ids outside [0,49408) are clamped (the host variant rejects them). */
 int sdb_clip_forward_dev(sdb_ctx* ctx, const int32_t* d_tokens, int n, int L, float* d_out, void* stream);
 
+/* ---- VAE encoder ---------------------------------------------------------------- */
+/* Autoencoder::encode_image (src/model/autoencoder/mod.rs:60-66): img [n,3,H,W] -> latent [n,4,H/8,W/8] = the first four
+ * channels of quant_conv(encoder(img)). H, W multiples of 8 (>= 64). Only img2img needs it; the reference CLI never calls it. */
+int sdb_encode_image(sdb_ctx* ctx, const float* img, int n, int H, int W, float* latent);
+int sdb_encode_image_dev(sdb_ctx* ctx, const float* d_img, int n, int H, int W, float* d_latent, void* stream);
+
 /* ---- hot path, device buffers (zero-copy callers) ------------------------------------------ */
 int sdb_unet_forward_dev(sdb_ctx* ctx, const float* d_x, int32_t timestep, const float* d_context,
                          int n, int H, int W, int L, float* d_out, void* stream);

@@ -360,6 +360,43 @@ def decode_latent(P, latent, taps=None, prefix="autoencoder"):
     return conv2d(P, f"{d}/conv_out", silu(group_norm(P, f"{d}/norm_out", x)), padding=1)
 
 
+def padded_conv2d_s2(P, name, x):
+    """reference autoencoder/mod.rs:340-412 with PaddingCfg(0,1,0,1), stride 2 (:229-236): a conv with symmetric padding
+    padding_actual = 2 whose output is sliced from index 1 -- i.e. pad bottom/right by one, no pad top/left."""
+    y = conv2d(P, f"{name}/conv", x, stride=2, padding=2)
+    hh, ww = x.shape[2] // 2, x.shape[3] // 2  # desired = (0 + 1 + H - 3) / 2 + 1
+    return y[:, :, 1:1 + hh, 1:1 + ww]
+
+
+def encode_image(P, img, taps=None, prefix="autoencoder"):
+    """reference autoencoder/mod.rs:60-66 (encode_image) + Encoder::forward :133-145 + EncoderBlock :255-265 + Mid :456-463.
+    img [n,3,H,W] -> latent [n,4,H/8,W/8] (the first 4 of quant_conv's 8 channels)."""
+    from stable_diffusion_burn_b200 import topology as T
+    e = f"{prefix}/encoder"
+    _enter("vae_enc/in")
+    x = conv2d(P, f"{e}/conv_in", img.to(P.dtype), padding=1)
+    nb = len(T.VAE_ENCODER_BLOCKS)
+    for i in range(nb):
+        b = f"{e}/blocks/{i}"
+        _enter(f"vae_enc/b{i}")
+        x = resnet_block(P, f"{b}/res1", x)
+        x = resnet_block(P, f"{b}/res2", x)
+        if i != nb - 1:
+            x = padded_conv2d_s2(P, f"{b}/downsampler", x)
+        if taps is not None:
+            taps[f"blocks/{i}"] = x
+    _enter("vae_enc/mid")
+    x = resnet_block(P, f"{e}/mid/block_1", x)
+    x = conv_self_attention_block(P, f"{e}/mid/attn", x)
+    x = resnet_block(P, f"{e}/mid/block_2", x)
+    if taps is not None:
+        taps["mid"] = x
+    _enter("vae_enc/out")
+    x = conv2d(P, f"{e}/conv_out", silu(group_norm(P, f"{e}/norm_out", x)), padding=1)
+    x = conv2d(P, f"{prefix}/quant_conv", x)
+    return x[:, 0:4]
+
+
 # -------------------------------------------------------------------- pipeline
 def forward_diffuser(P, latent, t, context, uncond, scale):
     """reference stablediffusion/mod.rs:162-192. `uncond` [Lu,768] is broadcast over the batch

@@ -28,6 +28,7 @@ extern "C" {
     fn sdb_load_dump_dir(ctx: *mut SdbCtx, path: *const c_char) -> c_int;
     fn sdb_finalize_weights(ctx: *mut SdbCtx) -> c_int;
     fn sdb_clip_forward(ctx: *mut SdbCtx, tokens: *const i32, n: c_int, l: c_int, out: *mut f32) -> c_int;
+    fn sdb_encode_image(ctx: *mut SdbCtx, img: *const f32, n: c_int, h: c_int, w: c_int, latent: *mut f32) -> c_int;
     fn sdb_unet_forward(ctx: *mut SdbCtx, x: *const f32, timestep: i32, context: *const f32, n: c_int, h: c_int,
                         w: c_int, l: c_int, out: *mut f32) -> c_int;
     fn sdb_decode_latent(ctx: *mut SdbCtx, latent: *const f32, n: c_int, h: c_int, w: c_int, img: *mut f32) -> c_int;
@@ -81,6 +82,13 @@ impl StableDiffusion {
 
     pub fn finalize_weights(&self) -> Result<(), SdbError> {
         self.check(unsafe { sdb_finalize_weights(self.ctx) })
+    }
+
+    /// `Autoencoder::encode_image(x)` (src/model/autoencoder/mod.rs:60-66): [n, 3, h, w] -> [n, 4, h/8, w/8].
+    pub fn encode_image(&self, img: &[f32], [n, h, w]: [usize; 3]) -> Result<Vec<f32>, SdbError> {
+        let mut latent = vec![0f32; n * 4 * (h / 8) * (w / 8)];
+        self.check(unsafe { sdb_encode_image(self.ctx, img.as_ptr(), n as c_int, h as c_int, w as c_int, latent.as_mut_ptr()) })?;
+        Ok(latent)
     }
 
     /// `CLIP::forward(tokens)` (src/model/clip/mod.rs:56-75): ids [n, l] (l <= 77, unpadded) -> [n, l, 768].

@@ -40,6 +40,8 @@ SIGNATURES = [
                                    C.c_uint64, C.c_int, C.c_int, _u8p]),
     ("sdb_load_dump_dir", C.c_int, [_ctx, C.c_char_p]),
     ("sdb_read_dump_tensor", C.c_int64, [C.c_char_p, C.c_int, C.POINTER(C.c_int64), _f32p, C.c_int64]),
+    ("sdb_encode_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _f32p]),
+    ("sdb_encode_image_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("sdb_clip_forward", C.c_int, [_ctx, C.POINTER(C.c_int32), C.c_int, C.c_int, _f32p]),
     ("sdb_clip_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("sdb_unet_forward_dev", C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -167,6 +169,14 @@ class Context:
 
     def load_dump_dir(self, path):
         self.check(self.lib.sdb_load_dump_dir(self.h, os.fsencode(path)))
+
+    def encode_image(self, img):
+        a = f32(img)
+        n, ch, H, W = a.shape
+        assert ch == 3
+        out = np.empty((n, 4, H // 8, W // 8), np.float32)
+        self.check(self.lib.sdb_encode_image(self.h, ptr(a), n, H, W, ptr(out)))
+        return out
 
     def clip_forward(self, tokens):
         t = np.ascontiguousarray(tokens, dtype=np.int32)

@@ -239,6 +239,21 @@ int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, con
   API_END
 }
 
+int sdb_encode_image(sdb_ctx* ctx, const float* img, int n, int H, int W, float* latent) {
+  API_BEGIN(ctx)
+  need_final(c);
+  SDB_CHECK(img && latent, "null argument");
+  model_encode_host(c, img, n, H, W, latent);
+  API_END
+}
+
+int sdb_encode_image_dev(sdb_ctx* ctx, const float* d_img, int n, int H, int W, float* d_latent, void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_encode_dev(c, d_img, n, H, W, d_latent, (cudaStream_t)stream);
+  API_END
+}
+
 int sdb_clip_forward(sdb_ctx* ctx, const int32_t* tokens, int n, int L, float* out) {
   API_BEGIN(ctx)
   need_final(c);

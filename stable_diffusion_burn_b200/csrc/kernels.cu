@@ -4,6 +4,8 @@
 // All activations are NHWC; loads/stores are 8- or 16-byte vectors, coalesced along channels.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace sdb {
 
 static inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
@@ -631,8 +633,33 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
     launch_k(conv3x3_small_cout_kernel<4>, grid, dim3(256), smem, st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
   else if (Cout == 3)
     launch_k(conv3x3_small_cout_kernel<3>, grid, dim3(256), smem, st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
+  else if (Cout == 8)
+    launch_k(conv3x3_small_cout_kernel<8>, grid, dim3(256), smem, st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
   else
-    throw Error("conv3x3_small_cout: Cout must be 3 or 4");
+    throw Error("conv3x3_small_cout: Cout must be 3, 4 or 8");
+  SDB_CUDA(cudaGetLastError());
+}
+
+// quant_conv (1x1, 8 -> 8) followed by the slice [0..4) of Autoencoder::encode_image (autoencoder/mod.rs:60-66): NCHW in/out
+__global__ void quant_conv_slice_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                        int HW, float* __restrict__ y) {
+  const int n = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = x[((size_t)n * 8 + j) * HW + p];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = b[c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += w[c * 8 + j] * v[j];
+      y[((size_t)n * 4 + c) * HW + p] = acc;
+    }
+  }
+}
+void quant_conv_slice_launch(const float* x, const float* w, const float* b, int n, int HW, float* y, cudaStream_t st) {
+  dim3 grid(std::min(ceil_div(HW, 256), 1024), n);
+  quant_conv_slice_kernel<<<grid, 256, 0, st>>>(x, w, b, HW, y);
   SDB_CUDA(cudaGetLastError());
 }
 

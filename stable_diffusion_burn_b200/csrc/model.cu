@@ -42,7 +42,7 @@ static float* mptr(Ctx& c, int idx) {
 static void pack_conv(Ctx& c, ConvW& w, bool up2 = false) {
   w.bias = mptr(c, w.bi);
   if (w.cin % 64 != 0 || w.cout % 32 != 0) {  // CUDA-core convs
-    if (w.cout <= 4 && w.k == 3) {
+    if (w.cout <= 8 && w.k == 3 && w.cin % 4 == 0) {
       w.w_small = c.packed.get<float>((size_t)w.cout * 9 * w.cin);
       pack_small_cout_launch(mptr(c, w.wi), w.cout, w.cin, w.w_small, c.stream);
     }
@@ -185,6 +185,24 @@ void model_finalize(Ctx& c) {
     if (m.dec[i].has_up) pack_conv(c, m.dec[i].up, /*up2=*/true), m.dec[i].up.passes = g_vae_passes_up;
   }
   pack_norm(c, m.vae_norm_out);
+  // ---- VAE encoder (row f4): every GEMM 3-term split-fp16 (runs once per image; no accuracy budget spent here)
+  {
+    EncoderW& e = m.enc;
+    pack_conv(c, e.conv_in), pack_conv(c, e.conv_out), pack_conv(c, e.quant);
+    // conv_in has 3 input channels: the Cin = 4 CUDA-core kernel gets weights padded with a zero fourth channel
+    e.conv_in_w4 = c.packed.get<float>((size_t)128 * 36);
+    SDB_CUDA(cudaMemsetAsync(e.conv_in_w4, 0, (size_t)128 * 36 * 4, c.stream));
+    SDB_CUDA(cudaMemcpy2DAsync(e.conv_in_w4, 36 * 4, mptr(c, e.conv_in.wi), 27 * 4, 27 * 4, 128, cudaMemcpyDeviceToDevice, c.stream));
+    for (int i = 0; i < 4; ++i) {
+      pack_resnet(c, e.blocks[i].res[0], 3), pack_resnet(c, e.blocks[i].res[1], 3);
+      if (e.blocks[i].has_down) pack_conv(c, e.blocks[i].down), e.blocks[i].down.passes = 3;
+    }
+    pack_resnet(c, e.mid_block1, 3), pack_resnet(c, e.mid_block2, 3);
+    pack_norm(c, e.mid_attn.norm);
+    pack_conv(c, e.mid_attn.q), pack_conv(c, e.mid_attn.k), pack_conv(c, e.mid_attn.v), pack_conv(c, e.mid_attn.proj_out);
+    e.mid_attn.passes = 3;
+    pack_norm(c, e.norm_out);
+  }
   // ---- CLIP text encoder
   for (ClipBlockW& cb : m.clip.blocks) {
     pack_norm(c, cb.attn_ln), pack_norm(c, cb.mlp_ln);
@@ -755,6 +773,64 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   c.work.off = mark0;
 }
 
+// ================================================================================ VAE encoder
+// Autoencoder::encode_image (autoencoder/mod.rs:60-66): Encoder::forward (:133-145) -> quant_conv -> channels [0,4).
+// d_img4: the image with a zero fourth plane [nb][4][H][W]; d_latent [nb][4][H/8][W/8].
+static void vae_encode(Fwd& f, const float* d_img4, int H, int W, float* d_latent) {
+  Ctx& c = f.c;
+  EncoderW& e = f.m.enc;
+  const size_t mark0 = c.work.off;
+  f.gn_slot = 0;
+  f.init_sums(40);
+  Act x = f.act(H, W, 128);
+  {
+    KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 27.0 * 128);
+    conv3x3_cin4_launch(d_img4, f.nb, H, W, e.conv_in_w4, e.conv_in.bias, 128, nullptr, nullptr, 1.f, x.p, Half2Ptr{}, c.stream);
+  }
+  // EncoderBlocks (:255-265): two ResnetBlocks, then the stride-2 conv padded bottom/right only
+  for (int i = 0; i < 4; ++i) {
+    EncoderBlockW& eb = e.blocks[i];
+    for (int j = 0; j < 2; ++j) {
+      Act o = f.act(H, W, eb.res[j].cout);
+      run_resnet(f, eb.res[j], x, o);
+      x = o;
+    }
+    if (eb.has_down) {
+      SDB_CHECK(H % 2 == 0 && W % 2 == 0, "encode_image: image height and width must be multiples of 8");
+      Act o = f.act(H / 2, W / 2, eb.down.cout);
+      const size_t mk = c.work.off;
+      ActOp a = f.raw_operand(x, nullptr, PREP_PHASE2, true);
+      Epilogue ep;
+      ep.out_f32 = o.p, ep.bias = eb.down.bias;
+      run_gemm(c, G_CONV3_S2_PAD01, a, nullptr, eb.down.packed, eb.down.passes, ep);
+      c.work.off = mk;
+      x = o;
+      H /= 2, W /= 2;
+    }
+  }
+  // Mid (:456-463)
+  {
+    Act a = f.act(H, W, 512), b = f.act(H, W, 512), d = f.act(H, W, 512);
+    run_resnet(f, e.mid_block1, x, a);
+    run_vae_attention(f, e.mid_attn, a, b);
+    run_resnet(f, e.mid_block2, b, d);
+    x = d;
+  }
+  // norm_out + SiLU + conv_out 512 -> 8 (fp32 CUDA cores, NCHW), then quant_conv 8 -> 8 and the slice [0,4)
+  float* y8 = c.work.get<float>((size_t)f.nb * 8 * H * W);
+  {
+    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
+    KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 512 * 8);
+    conv3x3_small_cout_launch(x.p, f.nb, H, W, 512, sums, e.norm_out.gamma, e.norm_out.beta, e.norm_out.eps, e.conv_out.w_small,
+                              e.conv_out.bias, 8, y8, c.stream);
+  }
+  {
+    KernelScope ks(c, KC_ELEMENTWISE);
+    quant_conv_slice_launch(y8, mptr(c, e.quant.wi), e.quant.bias, f.nb, H * W, d_latent, c.stream);
+  }
+  c.work.off = mark0;
+}
+
 // ================================================================================ public entry points
 namespace {
 struct StreamJoin {  // run on c.stream ordered after / before the caller's stream
@@ -866,6 +942,42 @@ void model_decode_host(Ctx& c, const float* latent, int n, int H, int W, float* 
     throw;
   }
   cudaFree(d_l), cudaFree(d_i);
+}
+
+void model_encode_dev(Ctx& c, const float* d_img, int n, int H, int W, float* d_latent, cudaStream_t caller) {
+  SDB_CHECK(n >= 1 && H >= 64 && W >= 64 && H % 8 == 0 && W % 8 == 0 && ((H / 8) * (W / 8)) % 8 == 0,
+            "encode_image: height and width must be multiples of 8, at least 64, with (H/8)*(W/8) a multiple of 8");
+  StreamJoin join(c, caller);
+  c.work.reset();
+  const size_t plane = (size_t)H * W;
+  for (int i0 = 0; i0 < n; i0 += 4) {  // chunks of 4 images bound the work arena like decode_chunked
+    const int nb = std::min(4, n - i0);
+    const size_t mark = c.work.off;
+    float* img4 = c.work.get<float>((size_t)nb * 4 * plane);
+    SDB_CUDA(cudaMemsetAsync(img4, 0, (size_t)nb * 4 * plane * 4, c.stream));
+    SDB_CUDA(cudaMemcpy2DAsync(img4, 4 * plane * 4, d_img + (size_t)i0 * 3 * plane, 3 * plane * 4, 3 * plane * 4, nb,
+                               cudaMemcpyDeviceToDevice, c.stream));
+    Fwd f(c, nb);
+    vae_encode(f, img4, H, W, d_latent + (size_t)i0 * 4 * (plane / 64));
+    c.work.off = mark;
+  }
+}
+
+void model_encode_host(Ctx& c, const float* img, int n, int H, int W, float* latent) {
+  const size_t ie = (size_t)n * 3 * H * W, le = (size_t)n * 4 * (H / 8) * (W / 8);
+  float *d_i = nullptr, *d_l = nullptr;
+  try {
+    SDB_CUDA(cudaMalloc(&d_i, ie * 4));
+    SDB_CUDA(cudaMalloc(&d_l, le * 4));
+    SDB_CUDA(cudaMemcpyAsync(d_i, img, ie * 4, cudaMemcpyHostToDevice, c.stream));
+    model_encode_dev(c, d_i, n, H, W, d_l, c.stream);
+    SDB_CUDA(cudaMemcpyAsync(latent, d_l, le * 4, cudaMemcpyDeviceToHost, c.stream));
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+  } catch (...) {
+    cudaFree(d_i), cudaFree(d_l);
+    throw;
+  }
+  cudaFree(d_i), cudaFree(d_l);
 }
 
 // latent_to_image (stablediffusion/mod.rs:69-100)

@@ -15,6 +15,8 @@ void model_unet_forward_dev(Ctx& c, const float* d_x, int t, const float* d_cont
                             float* d_out, cudaStream_t caller);
 void model_decode_host(Ctx& c, const float* latent, int n, int H, int W, float* img);
 void model_decode_dev(Ctx& c, const float* d_latent, int n, int H, int W, float* d_img, cudaStream_t caller);
+void model_encode_host(Ctx& c, const float* img, int n, int H, int W, float* latent);
+void model_encode_dev(Ctx& c, const float* d_img, int n, int H, int W, float* d_latent, cudaStream_t caller);
 void model_latent_to_image_host(Ctx& c, const float* latent, int n, int H, int W, uint8_t* rgb);
 void model_sample_host(Ctx& c, const float* context, int n, int L, const float* uncond, int Lu, double scale, int n_steps,
                        const float* init_latent, uint64_t seed, int H, int W, float* latent_out, uint8_t* rgb);

@@ -38,6 +38,20 @@ struct Builder {
     w.wi = add(name + "/weight", {cout, cin, k, k}, K_CONV_W, cin * k * k);
     w.bi = add(name + "/bias", {cout}, K_CONV_B, cin * k * k);
   }
+  // PaddedConv2d(0,1,0,1) stride 2 (save_padded_conv2d python/save.py:70-97): the Conv2d lives in <name>/conv and is saved
+  // with padding (0,0); channels / kernel_size / stride / padding sit beside it
+  void padded_conv_s2(ConvW& w, const std::string& name, int ch) {
+    w.cin = ch, w.cout = ch, w.k = 3;
+    const std::string cn = name + "/conv";
+    pair(cn + "/stride", 2.f, 2.f), pair(cn + "/padding", 0.f, 0.f), pair(cn + "/dilation", 1.f, 1.f);
+    pair(cn + "/kernel_size", 3.f, 3.f);
+    scalar(cn + "/n_group", 1.f), scalar(cn + "/n_channels_in", (float)ch), scalar(cn + "/n_channels_out", (float)ch);
+    pair(name + "/channels", (float)ch, (float)ch);
+    scalar(name + "/kernel_size", 3.f), scalar(name + "/stride", 2.f);
+    c.meta.push_back(MetaCheck{name + "/padding", {0.f, 1.f, 0.f, 1.f}, false});
+    w.wi = add(cn + "/weight", {ch, ch, 3, 3}, K_CONV_W, ch * 9);
+    w.bi = add(cn + "/bias", {ch}, K_CONV_B, ch * 9);
+  }
   void lin(LinW& w, const std::string& name, int in, int out, bool bias = true) {
     w.in = in, w.out = out;
     w.wi = add(name + "/weight", {in, out}, K_LIN_W, in);
@@ -207,6 +221,31 @@ void model_create(Ctx& c) {
   }
   b.norm(m->clip.ln_final, "clip/layer_norm", 768, false);
   b.scalar("clip/n_layer", 12.f);  // clip/load.rs:73
+  // ---- VAE encoder + quant_conv (autoencoder/mod.rs:31, 122-145, 249-266)
+  {
+    EncoderW& e = m->enc;
+    const std::string en = "autoencoder/encoder";
+    b.conv(e.conv_in, en + "/conv_in", 3, 128, 3);
+    static const int enc_ch[4][2] = {{128, 128}, {128, 256}, {256, 512}, {512, 512}};
+    for (int i = 0; i < 4; ++i) {
+      const std::string bn = en + "/blocks/" + std::to_string(i);
+      b.resnet(e.blocks[i].res[0], bn + "/res1", enc_ch[i][0], enc_ch[i][1]);
+      b.resnet(e.blocks[i].res[1], bn + "/res2", enc_ch[i][1], enc_ch[i][1]);
+      e.blocks[i].has_down = i != 3;
+      if (e.blocks[i].has_down) b.padded_conv_s2(e.blocks[i].down, bn + "/downsampler", enc_ch[i][1]);
+    }
+    b.resnet(e.mid_block1, en + "/mid/block_1", 512, 512);
+    b.norm(e.mid_attn.norm, en + "/mid/attn/norm", 512);
+    b.conv(e.mid_attn.q, en + "/mid/attn/q", 512, 512, 1);
+    b.conv(e.mid_attn.k, en + "/mid/attn/k", 512, 512, 1);
+    b.conv(e.mid_attn.v, en + "/mid/attn/v", 512, 512, 1);
+    b.conv(e.mid_attn.proj_out, en + "/mid/attn/proj_out", 512, 512, 1);
+    b.resnet(e.mid_block2, en + "/mid/block_2", 512, 512);
+    b.scalar(en + "/n_block", 4.f);  // autoencoder/load.rs:163
+    b.norm(e.norm_out, en + "/norm_out", 512);
+    b.conv(e.conv_out, en + "/conv_out", 512, 8, 3);
+    b.conv(e.quant, "autoencoder/quant_conv", 8, 8, 1);
+  }
   // ---- sampler schedule (stablediffusion/mod.rs:44)
   m->alphas_i = b.add("alpha_cumulative_products", {1000}, K_SCHED, 1);
 

@@ -86,6 +86,20 @@ struct DecoderBlockW {
   ConvW up;
 };
 
+struct EncoderBlockW {  // autoencoder/mod.rs:249-266
+  ResnetW res[2];
+  bool has_down = false;
+  ConvW down;  // PaddedConv2d(0,1,0,1) stride 2
+};
+struct EncoderW {       // autoencoder/mod.rs:122-145 + quant_conv (:60-66)
+  ConvW conv_in, conv_out, quant;
+  float* conv_in_w4 = nullptr;  // conv_in weights padded to 4 input channels (the Cin = 4 CUDA-core conv kernel)
+  EncoderBlockW blocks[4];
+  ResnetW mid_block1, mid_block2;
+  VaeAttnW mid_attn;
+  NormW norm_out;
+};
+
 struct ClipBlockW {  // src/model/clip/mod.rs:77-115
   NormW attn_ln, mlp_ln;
   LinW query, key, value, out, fc1, fc2;
@@ -101,6 +115,7 @@ struct ClipW {
 
 struct Model {
   ClipW clip;
+  EncoderW enc;
   // UNet
   LinW lin1_time, lin2_time;
   std::vector<UNetBlockW> in_blocks, out_blocks;

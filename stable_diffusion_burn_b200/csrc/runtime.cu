@@ -233,6 +233,17 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
         p.tap_ph[t] = (kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0);
       }
       break;
+    case G_CONV3_S2_PAD01:
+      // input row 2y + kh: kh = 0 even row y, kh = 1 odd row y, kh = 2 even row y + 1 (row H is the zero pad: TMA OOB fill)
+      SDB_CHECK(a0.P == 4, "stride-2 conv needs a 4-phase operand");
+      p.num_taps = 9;
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t % 3;
+        p.tap_dh[t] = kh == 2 ? 1 : 0;
+        p.tap_dw[t] = kw == 2 ? 1 : 0;
+        p.tap_ph[t] = (kh == 1 ? 2 : 0) + (kw == 1 ? 1 : 0);
+      }
+      break;
     case G_CONV3_UP2:
       p.num_taps = 4;
       phases_out = 4;

@@ -67,7 +67,9 @@ struct WeightOp {
   long long ld = 0;  // row stride in elements (0 -> K)
   int rows = 0;      // rows that really exist (0 -> N); rows in [rows, N) read as zero (TMA OOB fill)
 };
-enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4 };
+// G_CONV3_S2: 3x3 stride 2 pad 1 (UNet downsample); G_CONV3_S2_PAD01: 3x3 stride 2 padded bottom/right only
+// (the VAE encoder's PaddedConv2d(0,1,0,1), autoencoder/mod.rs:229-236). Both read a 4-phase-plane operand.
+enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4, G_CONV3_S2_PAD01 = 5 };
 
 struct Epilogue {
   float* out_f32 = nullptr;

@@ -82,7 +82,15 @@ def save_dump_dir(root: str, params: dict, eps: float | dict = 1e-5) -> None:
         if kind == "conv_w":
             cout, cin, k, _ = shape
             s = conv_stride(name)
-            for fname, val in (("stride", s), ("padding", k // 2), ("dilation", 1), ("kernel_size", k)):
+            pad = k // 2
+            if d.endswith("/downsampler/conv"):  # save_padded_conv2d (python/save.py:70-97): inner conv saved with padding (0,0)
+                s, pad = 2, 0
+                outer = os.path.dirname(path)
+                save_tensor(np.array([cin, cout], np.float32), "channels", outer)
+                save_scalar(k, "kernel_size", outer)
+                save_scalar(2, "stride", outer)
+                save_tensor(np.array([0, 1, 0, 1], np.float32), "padding", outer)
+            for fname, val in (("stride", s), ("padding", pad), ("dilation", 1), ("kernel_size", k)):
                 save_tensor(np.array([val, val], np.float32), fname, path)
             save_scalar(1, "n_group", path)
             save_scalar(cin, "n_channels_in", path)
@@ -99,8 +107,9 @@ def save_dump_dir(root: str, params: dict, eps: float | dict = 1e-5) -> None:
             d = name[: -len("/query/weight")]
             os.makedirs(os.path.join(root, d), exist_ok=True)
             save_scalar(12 if d.startswith("clip/") else 8, "n_head", os.path.join(root, d))
-    for d in ("clip", "autoencoder/decoder"):
+    for d in ("clip", "autoencoder/decoder", "autoencoder/encoder"):
         os.makedirs(os.path.join(root, d), exist_ok=True)
+    save_scalar(4, "n_block", os.path.join(root, "autoencoder/encoder"))
     save_scalar(12, "n_layer", os.path.join(root, "clip"))
     save_scalar(4, "n_block", os.path.join(root, "autoencoder/decoder"))
 

@@ -38,6 +38,14 @@ class Autoencoder:
         """latent [n,4,H,W] -> image [n,3,8H,8W]."""
         return self._c.decode_latent(latent)
 
+    def encode_image(self, img: np.ndarray) -> np.ndarray:
+        """Autoencoder::encode_image (src/model/autoencoder/mod.rs:60-66): image [n,3,H,W] -> latent [n,4,H/8,W/8]."""
+        return self._c.encode_image(img)
+
+    def forward(self, img: np.ndarray) -> np.ndarray:
+        """Autoencoder::forward (:56-58) = decode_latent(encode_image(x))."""
+        return self.decode_latent(self.encode_image(img))
+
 
 class CLIP:
     def __init__(self, ctx: Context):

@@ -161,6 +161,34 @@ def vae_decoder_params(prefix="autoencoder"):
     return out
 
 
+VAE_ENCODER_BLOCKS = [(128, 128), (128, 256), (256, 512), (512, 512)]  # autoencoder/mod.rs:31
+
+
+def vae_encoder_params(prefix="autoencoder"):
+    """VAE encoder + quant_conv: autoencoder/mod.rs:60-66, 122-145, 249-266; names from
+    autoencoder/load.rs:100-181. Shapes are the SD-v1 ones a dump carries (mid / norm_out / conv_out at 512 channels);
+    EncoderConfig::init would size them from channels.first().0 = 128 (:84), which no loaded model uses."""
+    out = []
+    e = f"{prefix}/encoder"
+    _conv(out, f"{e}/conv_in", 3, 128, 3)
+    for i, (cin, cout) in enumerate(VAE_ENCODER_BLOCKS):
+        b = f"{e}/blocks/{i}"
+        _resnet(out, f"{b}/res1", cin, cout)
+        _resnet(out, f"{b}/res2", cout, cout)
+        if i != len(VAE_ENCODER_BLOCKS) - 1:
+            _conv(out, f"{b}/downsampler/conv", cout, cout, 3)  # PaddedConv2d (0,1,0,1), stride 2 (:229-236)
+    _resnet(out, f"{e}/mid/block_1", 512, 512)
+    a = f"{e}/mid/attn"
+    _norm(out, f"{a}/norm", 512)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(out, f"{a}/{n}", 512, 512, 1)
+    _resnet(out, f"{e}/mid/block_2", 512, 512)
+    _norm(out, f"{e}/norm_out", 512)
+    _conv(out, f"{e}/conv_out", 512, 8, 3)
+    _conv(out, f"{prefix}/quant_conv", 8, 8, 1)
+    return out
+
+
 CLIP_VOCAB, CLIP_STATE, CLIP_HEADS, CLIP_CTX, CLIP_LAYERS = 49408, 768, 12, 77, 12  # stablediffusion/mod.rs:29
 
 
@@ -182,7 +210,7 @@ def clip_params(prefix="clip"):
 
 
 def all_params():
-    return unet_params() + vae_decoder_params() + clip_params()
+    return unet_params() + vae_decoder_params() + clip_params() + vae_encoder_params()
 
 
 if __name__ == "__main__":

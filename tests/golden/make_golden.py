@@ -46,9 +46,34 @@ def clip_golden():
     np.savez_compressed(os.path.join(OUT, "clip.npz"), **keep)
 
 
+def enc_images():
+    """Inputs of the VAE-encoder fixture: the RNG-free ramp at 64x64 and a seeded batch of two 128x96 images."""
+    g = np.random.Generator(np.random.Philox(777))
+    return {"ramp64": synth.sin_ramp((1, 3, 64, 64)), "randn128x96": g.standard_normal((2, 3, 128, 96), dtype=np.float32)}
+
+
+def enc_golden():
+    from stable_diffusion_burn_b200 import topology
+    P = O.Params(synth.make_params(0, which=topology.vae_encoder_params()))
+    keep = {}
+    with torch.no_grad():
+        for name, img in enc_images().items():
+            taps = {}
+            y = O.encode_image(P, torch.from_numpy(img), taps=taps)
+            keep["img:" + name] = img
+            keep["lat:" + name] = y.numpy()
+            keep["mid:" + name] = taps["mid"].numpy()
+            print("vae_enc", name, tuple(y.shape), "rms", float(y.pow(2).mean().sqrt()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "vae_enc.npz"), **keep)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
+    if not ONLY or "enc" in ONLY:
+        enc_golden()
+        if ONLY == {"enc"}:
+            return
     if not ONLY or "clip" in ONLY:
         clip_golden()
         if ONLY == {"clip"}:
