@@ -40,7 +40,6 @@ struct GemmParams {
   int geglu;               // 1: columns are (x|gate) interleaved per tile, output width N/2
   long long* dbg;          // SDB_GEMM_DBG: 8 clock64 stamps of CTA (0,0,0) (entry, prologue done, first TMA issued, first
                            // operands landed, last MMA issued, accumulator ready, epilogue stores done, exit)
-  int dbg_mode;            // SDB_GEMM_DBG_MODE (bring-up): 1 = skip the output stores, 2 = skip staging + stores
   int pdl_late;            // 1: release the dependent launch when the epilogue starts instead of at kernel entry
   int act;                 // 1: QuickGELU x*sigmoid(1.702x) on the result (CLIP MLP, clip/mod.rs:224-226)
   float* ws;               // split-K workspace [split][M][N]

@@ -783,24 +783,6 @@ void to_rgb8_launch(const float* img_nchw, int n, int H, int W, uint8_t* rgb, cu
   SDB_CUDA(cudaGetLastError());
 }
 
-__global__ void scale_kernel(const float* __restrict__ x, float s, long long count, float* __restrict__ y) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
-    y[i] = x[i] * s;
-}
-__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = a[i] + b[i];
-}
-void add_vec_launch(const float* a, const float* b, int n, float* y, cudaStream_t st) {
-  add_vec_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, n, y);
-  SDB_CUDA(cudaGetLastError());
-}
-void scale_launch(const float* x, float s, long long count, float* y, cudaStream_t st) {
-  int grid = (int)((count + 255) / 256);
-  if (grid > 148 * 8) grid = 148 * 8;
-  scale_kernel<<<grid, 256, 0, st>>>(x, s, count, y);
-  SDB_CUDA(cudaGetLastError());
-}
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;

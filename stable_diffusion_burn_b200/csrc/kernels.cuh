@@ -76,7 +76,6 @@ void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long
 // u8 = trunc(clamp((img+1)/2*255, 0, 255)), NCHW fp32 -> NHWC u8 (reference stablediffusion/mod.rs:79-97)
 void to_rgb8_launch(const float* img_nchw, int n, int H, int W, uint8_t* rgb, cudaStream_t st);
 void quant_conv_slice_launch(const float* x, const float* w, const float* b, int n, int HW, float* y, cudaStream_t st);
-void scale_launch(const float* x, float s, long long count, float* y, cudaStream_t st);
 void add_vec_launch(const float* a, const float* b, int n, float* y, cudaStream_t st);
 // N(0,1) latents from a Philox-like counter hash (used only when the caller passes no init latent)
 void randn_launch(float* x, long long count, uint64_t seed, cudaStream_t st);

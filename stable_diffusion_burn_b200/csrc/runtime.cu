@@ -327,10 +327,6 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.geglu = ep.geglu;
   p.act = ep.act;
   p.pdl_late = g_pdl_late;
-  {
-    static const int dbg_mode = getenv("SDB_GEMM_DBG_MODE") ? atoi(getenv("SDB_GEMM_DBG_MODE")) : 0;
-    p.dbg_mode = dbg_mode;
-  }
   const int nout = ep.geglu ? w.N / 2 : w.N;
   p.ldc = ep.ldc ? ep.ldc : nout;
   p.ldc16 = ep.ldc16 ? ep.ldc16 : nout;
