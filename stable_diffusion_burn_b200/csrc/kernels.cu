@@ -738,6 +738,16 @@ void embed_tokens_launch(const int* tok, const float* E, const float* Pos, int n
   launch_k(embed_tokens_kernel, dim3(n * Lp), dim3(192), 0, st, tok, E, Pos, L, Lp, D, vocab, x);
 }
 
+// y = a + b (merged conv biases at finalize)
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+void add_vec_launch(const float* a, const float* b, int n, float* y, cudaStream_t st) {
+  add_vec_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, n, y);
+  SDB_CUDA(cudaGetLastError());
+}
+
 // ============================================================ sampler elementwise
 __global__ void cfg_ddim_kernel(const float* __restrict__ eu, const float* __restrict__ ec, float* __restrict__ lat,
                                 long long count, float scale, float sqrt_1m_at, float sqrt_at, float sqrt_aprev,
