@@ -140,6 +140,40 @@ def cpu_port_times(n_steps=1, budget_s=30.0):
     return steps, dec, threads, what
 
 
+def gpu_eager_times():
+    """OPTIONAL, labelled secondary comparator: the same torch restatement with its tensors on cuda:0, i.e. what
+    torch 2.11 eager (cuDNN convs with TF32 allowed, cuBLAS fp32 matmuls, materialised attention scores) does with the
+    reference's op sequence on this GPU. It is NOT the reference (which cannot be built here) and not this repo's path."""
+    import torch
+
+    from oracle import sd_oracle as O
+    from stable_diffusion_burn_b200 import synth
+    dev = torch.device("cuda:0")
+    P = O.Params({})
+    P.t = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_params(0).items()}
+    ctx = torch.from_numpy(synth.make_context(1, 77)).to(dev)
+    unc = torch.from_numpy(synth.make_context(1, 2, seed=99))[0].to(dev)
+    lat = torch.from_numpy(synth.make_latent(1, 64, 64)).to(dev)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    with torch.no_grad():
+        step_ms = timed(lambda: O.forward_diffuser(P, lat, 999, ctx, unc, 7.5), 5)
+        dec_ms = timed(lambda: O.decode_latent(P, lat * (1.0 / 0.18215)), 3)
+    return {"ms_per_ddim_step": step_ms, "ms_decode": dec_ms, "images_per_s": 1000.0 / (20 * step_ms + dec_ms),
+            "what": "torch 2.11 eager on cuda:0 running the oracle's op sequence (cuDNN conv, TF32 allowed; cuBLAS fp32 matmul): "
+                    "a labelled secondary comparator, not the reference and not this repo's path"}
+
+
 def run_reference(args):
     """Reference arm: the reference's own implementation cannot be built here (Rust, no toolchain), so this times
     the CPU port. Each bench step = one DDIM step (2 UNet evals) — a bounded sample of the 20-step workload."""
@@ -163,6 +197,11 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.ref_cuda:
+        try:
+            line["secondary_gpu_eager"] = gpu_eager_times()
+        except Exception as e:  # the comparator is optional: never let it take the reference line down
+            line["secondary_gpu_eager"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 
@@ -179,6 +218,8 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 = per-layer policy (meets 1e-3), 1/2/3 = force passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--ref-cuda", action="store_true",
+                    help="with --impl reference: also time the torch restatement on cuda:0 (labelled secondary comparator)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -255,7 +255,7 @@ def unet_forward(P, x, t, context, taps=None, prefix="unet"):
     x = x.to(P.dtype)
     context = context.to(P.dtype)
     _enter("emb")
-    t_emb = timestep_embedding(int(t), 320, 10000, P.dtype)
+    t_emb = timestep_embedding(int(t), 320, 10000, P.dtype).to(x.device)
     emb = linear(P, f"{prefix}/lin1_time_embed", t_emb)
     emb = silu(emb)
     emb = linear(P, f"{prefix}/lin2_time_embed", emb)
