@@ -39,3 +39,21 @@ def test_cleaning_quirks(tok):
     assert len(tok.encode("cat " * 100)) == 100
     # round trip of non-ASCII bytes through the byte<->unicode table
     assert tok.decode(tok.encode("café ☕")).strip() == "café ☕"
+
+
+def test_agrees_with_an_independent_clip_tokenizer(tok, tmp_path):
+    """Second opinion on the mirror: transformers.CLIPTokenizer (independently written from the same published BPE) built from the
+    same merges file must produce the same ids on plain prompts (no ftfy-specific cleaning involved)."""
+    tr = pytest.importorskip("transformers")
+    import json
+    merges = open(VOCAB, encoding="utf-8").read().split("\n")[1:49152 - 256 - 2 + 1]
+    vocab = [u for _, u in T._byte_unicode_table()]
+    vocab = vocab + [v + "</w>" for v in vocab] + ["".join(m.split()) for m in merges] + ["<|startoftext|>", "<|endoftext|>"]
+    (tmp_path / "vocab.json").write_text(json.dumps({v: i for i, v in enumerate(vocab)}))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(merges) + "\n", encoding="utf-8")
+    hf = tr.CLIPTokenizer(str(tmp_path / "vocab.json"), str(tmp_path / "merges.txt"))
+    prompts = ["An ancient mossy stone.", "a photograph of an astronaut riding a horse", "Hello world!  multiple   spaces",
+               "it's a dog's life, isn't it? 123 4567", "UPPER lower MiXeD", "oil painting, trending on artstation; 4k --hd",
+               "café naïve résumé", "a cat\nwith\ttabs", "x" * 40, "don't we'll they've I'm you're he'd"]
+    for p in prompts:
+        assert tok.encode(p) == hf(p, add_special_tokens=False)["input_ids"], p
