@@ -95,7 +95,8 @@ class Params:
 # ------------------------------------------------------------------ primitives
 def linear(P, name, x):
     """burn nn::Linear: y = x W + b, W stored [in,out] (reference src/model/load.rs:65-76)."""
-    y = _q(x, "a") @ _q(P(f"{name}/weight"), "w")
+    xa = x if id(x) in _EMU.get("pre_rounded", ()) else _q(x, "a")  # see nn_layer_norm: LN-fused emulation
+    y = xa @ _q(P(f"{name}/weight"), "w")
     if P.has(f"{name}/bias"):
         y = y + P(f"{name}/bias")
     return y
@@ -133,6 +134,14 @@ def nn_layer_norm(P, name, x, eps=1e-5):
     """burn nn::LayerNorm (third-party): biased variance, eps inside sqrt, affine."""
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    if _EMU.get("ln_fused") and _EMU["mode"] is not None:
+        # design study (not a product path): LayerNorm folded into the consuming GEMM as a rank-1 correction. The GEMM then reads
+        # the RAW x rounded to the operand format and the exact row statistics are applied in its epilogue, which equals
+        # normalising the rounded x with the exact statistics; the consumer must not round this tensor again.
+        h = (_q(x, "a") - mu) / (var + P.norm_eps.get(name, eps)).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
+        _EMU.setdefault("pre_rounded", set()).add(id(h))
+        _EMU.setdefault("keep", []).append(h)  # keep the object alive so its id stays unique
+        return h
     return (x - mu) / (var + P.norm_eps.get(name, eps)).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
 
 
