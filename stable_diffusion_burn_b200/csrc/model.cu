@@ -251,7 +251,7 @@ struct Fwd {
   void init_sums(int slots) {
     gn_slots = slots;
     gn_sums = c.work.get<double>((size_t)slots * nb * 64);
-    gn_tickets = c.work.get<unsigned int>((size_t)slots * nb * 2);  // tickets | flags
+    gn_tickets = c.work.get<unsigned int>((size_t)slots * nb * 2);  // one ticket counter per (slot, image); the second half is spare
     SDB_CUDA(cudaMemsetAsync(gn_tickets, 0, sizeof(unsigned int) * slots * nb * 2, c.stream));
   }
   // GroupNorm statistics of cat(x0,x1): returns the [nb][32][2] sums

@@ -420,7 +420,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
                 dbg_buf[11] - dbg_buf[10], dbg_buf[12] - dbg_buf[10], dbg_buf[13] - dbg_buf[12], dbg_buf[14] - dbg_buf[13]);
       }
     }
-    // (the split-K reduction happens inside the kernel: the last CTA of a tile folds the partials)
+    // (the split-K reduction happens inside the kernel: after a ticket rendezvous every split CTA folds its slice of the tile rows)
   }
 }
 
