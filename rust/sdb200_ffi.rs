@@ -6,8 +6,10 @@
 //!
 //!   let images = sd.sample_image(context, unconditional_context, scale, n_steps);
 //! becomes
-//!   let images = sdb200::StableDiffusion::new(0)?.load_dump(&model_name)?
-//!       .sample_image(&context_f32, [n, l], &uncond_f32, lu, scale, n_steps, None, 0)?;
+//!   let sdb = sdb200::StableDiffusion::new(0)?;
+//!   sdb.load_dump_dir(&model_name)?;          // in place of load_stable_diffusion(&model_name, &device)
+//!   sdb.finalize_weights()?;
+//!   let images = sdb.sample_image(&context_f32, [n, l], &uncond_f32, lu, scale, n_steps, None, 0)?;
 //!
 //! The signatures keep the reference's argument meaning (src/model/stablediffusion/mod.rs:51-57,
 //! src/model/unet/mod.rs:109-114, src/model/autoencoder/mod.rs:68) with plain fp32 slices in place of
