@@ -67,6 +67,14 @@ int sdb_init_synthetic(sdb_ctx* ctx, uint32_t seed);
 /* fp32 master arena (device pointer, bytes): one contiguous block holding every tensor, for the
  * single init-time ncclBroadcast from rank 0. */
 int sdb_weight_arena(sdb_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* Multi-GPU init: the ONE collective of the path. Rank 0 obtains an id with sdb_nccl_unique_id (128 bytes,
+ * = ncclUniqueId) and hands it to every rank by its own means (file, socket, MPI, torch store); then every rank calls
+ * sdb_broadcast_weights(ctx, id, rank, world): ncclCommInitRank + ncclBroadcast of the fp32 master arena (and of the per-norm
+ * eps table a dump-dir carries) from rank 0 over NVLink, then the communicator is destroyed — no collective on the sampling
+ * path. NCCL is resolved with dlopen("libnccl.so.2") at the first call: single-GPU hosts need no NCCL. world == 1 is a no-op.
+ * Call sdb_finalize_weights afterwards on every rank. */
+int sdb_nccl_unique_id(void* id128);
+int sdb_broadcast_weights(sdb_ctx* ctx, const void* id128, int rank, int world);
 /* Packs the master weights into kernel layouts (fp16 K-major tiles, fused QKV/GEGLU orders).
  * Must be called after the last sdb_set_tensor / broadcast and before any compute call. */
 int sdb_finalize_weights(sdb_ctx* ctx);
@@ -85,6 +93,13 @@ int sdb_decode_latent(sdb_ctx* ctx, const float* latent, int n, int H, int W, fl
 int sdb_sample_latent(sdb_ctx* ctx, const float* context, int n, int L, const float* uncond, int Lu,
                       double guidance_scale, int n_steps, const float* init_latent, uint64_t seed,
                       int H, int W, float* latent_out);
+/* StableDiffusion::forward_diffuser (src/model/stablediffusion/mod.rs:162-192): classifier-free guidance at one timestep,
+ * pred = u + (c - u) * scale with u = UNet(latent, t, uncond broadcast over the batch), c = UNet(latent, t, context) — evaluated
+ * as ONE batch-2n UNet pass (the pass sample_latent replays per step). latent [n,4,H,W]; pred / out_uncond / out_cond [n,4,H,W],
+ * each may be NULL (out_uncond / out_cond expose the two UNet outputs before the combine, for per-step parity checks). */
+int sdb_forward_diffuser(sdb_ctx* ctx, const float* latent, int32_t timestep, const float* context, int n, int L,
+                         const float* uncond, int Lu, double guidance_scale, int H, int W, float* pred,
+                         float* out_uncond, float* out_cond);
 /* StableDiffusion::latent_to_image (src/model/stablediffusion/mod.rs:69-100): decode(latent/0.18215),
  * (x+1)/2*255, NHWC, clamp to [0,255], truncate to u8. rgb [n,8H,8W,3]. */
 int sdb_latent_to_image(sdb_ctx* ctx, const float* latent, int n, int H, int W, uint8_t* rgb);
@@ -111,6 +126,8 @@ int sdb_encode_image_dev(sdb_ctx* ctx, const float* d_img, int n, int H, int W, 
 int sdb_unet_forward_dev(sdb_ctx* ctx, const float* d_x, int32_t timestep, const float* d_context,
                          int n, int H, int W, int L, float* d_out, void* stream);
 int sdb_decode_latent_dev(sdb_ctx* ctx, const float* d_latent, int n, int H, int W, float* d_img, void* stream);
+int sdb_forward_diffuser_dev(sdb_ctx* ctx, const float* d_latent, int32_t timestep, const float* d_context, int n, int L,
+                             const float* d_uncond, int Lu, double guidance_scale, int H, int W, float* d_pred, void* stream);
 int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, const float* d_uncond, int Lu,
                          double guidance_scale, int n_steps, const float* d_init_latent,
                          int H, int W, uint8_t* d_rgb, void* stream);
@@ -135,6 +152,12 @@ int64_t sdb_launch_count(sdb_ctx* ctx);
  * Exercises the tcgen05 GEMM exactly as the Linear layers use it. */
 int sdb_test_linear(sdb_ctx* ctx, const float* a, const float* w, const float* bias, int M, int K, int N,
                     int passes, float* c);
+/* The GEMM's other epilogues and K-loop forms, each reachable in isolation: out = A[M,K] x W[K,N] (+ bias) (+ residual[M,N])
+ * (+ XA[M,XK] x XW[XK,N], the "extra K" operands the ResBlock skip conv rides on). flags: 1 = GEGLU (W = [K][x | gate], out
+ * [M, N/2] = (x + b_x) * gelu_erf(gate + b_g), unet/mod.rs:578-592); 4 = read the result back from the fp16 hi + lo outputs.
+ * Split-K is chosen by the library's own policy (small M x N grid, K >= 2048). */
+int sdb_test_gemm_ex(sdb_ctx* ctx, const float* a, const float* w, const float* bias, const float* residual, int M, int K,
+                     int N, int passes, int flags, const float* xa, const float* xw, int XK, float* out);
 /* conv2d NCHW fp32 in/out through the implicit-GEMM path (3x3 pad 1 stride 1|2, or 1x1). */
 int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* bias, int n, int cin, int H,
                     int W, int cout, int ksize, int stride, int upsample, int passes, float* y);

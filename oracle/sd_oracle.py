@@ -145,8 +145,21 @@ def nn_layer_norm(P, name, x, eps=1e-5):
     return (x - mu) / (var + P.norm_eps.get(name, eps)).sqrt() * P(f"{name}/weight") + P(f"{name}/bias")
 
 
+_GELU = {"form": "erf"}
+
+
+def set_gelu_form(form):
+    """'erf' (burn nn::Gelu, the parity target) | 'tanh' (tinygrad 0.9.2's Tensor.gelu, python/dump.py:203-210).
+    'tanh' exists ONLY so that tests/test_ref_pin_cpu.py can compare this oracle with the reference's Python twin, whose GEGLU
+    uses the tanh approximation; every fixture the CUDA path is held to is generated with 'erf'."""
+    assert form in ("erf", "tanh")
+    _GELU["form"] = form
+
+
 def gelu_erf(x):
     """burn nn::Gelu = exact erf GELU (used at unet/mod.rs:590)."""
+    if _GELU["form"] == "tanh":
+        return 0.5 * x * (1.0 + torch.tanh(x * 0.7978845608 * (1.0 + 0.044715 * x * x)))
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
@@ -407,13 +420,16 @@ def encode_image(P, img, taps=None, prefix="autoencoder"):
 
 
 # -------------------------------------------------------------------- pipeline
-def forward_diffuser(P, latent, t, context, uncond, scale):
+def forward_diffuser(P, latent, t, context, uncond, scale, taps=None):
     """reference stablediffusion/mod.rs:162-192. `uncond` [Lu,768] is broadcast over the batch
-    (the evident intent of `.unsqueeze().repeat(&[0, n_batch])`)."""
+    (the evident intent of `.unsqueeze().repeat(&[0, n_batch])`).
+    `taps`: optional dict receiving the two UNet outputs ("uncond", "cond") before the guidance combine."""
     n = latent.shape[0]
     u_ctx = uncond.unsqueeze(0).repeat(n, 1, 1)
     u = unet_forward(P, latent, t, u_ctx)
     c = unet_forward(P, latent, t, context)
+    if taps is not None:
+        taps["uncond"], taps["cond"] = u, c
     return u + (c - u) * scale
 
 
@@ -435,7 +451,12 @@ def sample_latent(P, context, uncond, scale, n_steps, init_latent, taps=None):
         a_t = float(alphas[t])
         a_prev = float(alphas[t - step]) if t >= step else 1.0
         sqrt_noise = math.sqrt(1.0 - a_t)
-        pred = forward_diffuser(P, latent, t, context, uncond, scale)
+        dtaps = {} if taps is not None else None
+        if taps is not None:
+            taps[f"step{i}/latent_in"] = latent
+        pred = forward_diffuser(P, latent, t, context, uncond, scale, taps=dtaps)
+        if taps is not None:
+            taps[f"step{i}/uncond"], taps[f"step{i}/cond"] = dtaps["uncond"], dtaps["cond"]
         predx0 = (latent - pred * sqrt_noise) / math.sqrt(a_t)
         dir_latent = pred * math.sqrt(1.0 - a_prev - sigma * sigma)
         latent = predx0 * math.sqrt(a_prev) + dir_latent  # + gen_noise()*sigma, sigma == 0

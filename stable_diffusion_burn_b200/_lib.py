@@ -39,6 +39,14 @@ SIGNATURES = [
     ("sdb_sample_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_double, C.c_int, _f32p,
                                    C.c_uint64, C.c_int, C.c_int, _u8p]),
     ("sdb_load_dump_dir", C.c_int, [_ctx, C.c_char_p]),
+    ("sdb_nccl_unique_id", C.c_int, [C.c_void_p]),
+    ("sdb_broadcast_weights", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int]),
+    ("sdb_forward_diffuser", C.c_int, [_ctx, _f32p, C.c_int32, _f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_double, C.c_int,
+                                       C.c_int, _f32p, _f32p, _f32p]),
+    ("sdb_forward_diffuser_dev", C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("sdb_test_gemm_ex", C.c_int, [_ctx, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
+                                   C.c_int, _f32p]),
     ("sdb_read_dump_tensor", C.c_int64, [C.c_char_p, C.c_int, C.POINTER(C.c_int64), _f32p, C.c_int64]),
     ("sdb_encode_image", C.c_int, [_ctx, _f32p, C.c_int, C.c_int, C.c_int, _f32p]),
     ("sdb_encode_image_dev", C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -167,6 +175,24 @@ class Context:
         self.check(self.lib.sdb_unet_forward(self.h, ptr(x), int(t), ptr(context), n, H, W, L, ptr(out)))
         return out
 
+    def forward_diffuser(self, latent, t, context, uncond, scale):
+        """-> (pred, uncond UNet output, cond UNet output), each [n,4,H,W]."""
+        latent = f32(latent); context = f32(context); uncond = f32(uncond)
+        n, _, H, W = latent.shape
+        outs = [np.empty_like(latent) for _ in range(3)]
+        self.check(self.lib.sdb_forward_diffuser(self.h, ptr(latent), int(t), ptr(context), n, context.shape[1], ptr(uncond),
+                                                 uncond.shape[0], float(scale), H, W, ptr(outs[0]), ptr(outs[1]), ptr(outs[2])))
+        return tuple(outs)
+
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.sdb_nccl_unique_id(buf) != 0:
+            raise SdbError(self.lib.sdb_last_error(None).decode())
+        return buf.raw
+
+    def broadcast_weights(self, unique_id: bytes, rank: int, world: int):
+        self.check(self.lib.sdb_broadcast_weights(self.h, C.create_string_buffer(unique_id, 128), rank, world))
+
     def load_dump_dir(self, path):
         self.check(self.lib.sdb_load_dump_dir(self.h, os.fsencode(path)))
 
@@ -251,6 +277,20 @@ class Context:
         out = np.empty((M, N), np.float32)
         b = f32(bias) if bias is not None else None
         self.check(self.lib.sdb_test_linear(self.h, ptr(a), ptr(w), ptr(b) if b is not None else None, M, K, N, passes, ptr(out)))
+        return out
+
+    def test_gemm_ex(self, a, w, bias=None, residual=None, passes=1, geglu=False, from_f16=False, xa=None, xw=None):
+        a = f32(a); w = f32(w)
+        M, K = a.shape; N = w.shape[1]
+        out = np.empty((M, N // 2 if geglu else N), np.float32)
+        opt = lambda v: (None, None) if v is None else (f32(v), ptr(f32(v)))
+        keep = [opt(bias), opt(residual), opt(xa), opt(xw)]
+        for i, (arr, _) in enumerate(keep):  # keep the contiguous copies alive across the call
+            if arr is not None:
+                keep[i] = (arr, ptr(arr))
+        XK = 0 if xa is None else keep[2][0].shape[1]
+        self.check(self.lib.sdb_test_gemm_ex(self.h, ptr(a), ptr(w), keep[0][1], keep[1][1], M, K, N, passes,
+                                             (1 if geglu else 0) | (4 if from_f16 else 0), keep[2][1], keep[3][1], XK, ptr(out)))
         return out
 
     def test_conv2d(self, x, w, bias=None, stride=1, upsample=0, passes=1):

@@ -1,6 +1,8 @@
 // api.cu — extern "C" boundary (include/sdb200.h). No exception crosses it.
 #include "../../include/sdb200.h"
 
+#include <dlfcn.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -35,9 +37,61 @@ static thread_local std::string g_err;
   }                                          \
   return 0;
 
+// one teardown for sdb_destroy and for a failed sdb_create (a context holds ~35 GB of device memory)
+static void ctx_teardown(sdb_ctx* h) {
+  if (!h) return;
+  cudaSetDevice(h->c.device);
+  cudaDeviceSynchronize();
+  model_destroy(h->c);
+  h->c.io_destroy();
+  h->c.master.destroy();
+  h->c.packed.destroy();
+  h->c.work.destroy();
+  if (h->c.stream) cudaStreamDestroy(h->c.stream);
+  h->c.stream = nullptr;
+  delete h;
+}
+
+// ------------------------------------------------------------------------------ NCCL, resolved at run time
+// The library has no link-time dependency on NCCL: libnccl.so.2 is dlopen'ed by the first multi-GPU call (inside a torch
+// process this binds to the copy torch already loaded, same SONAME). Only the four entry points used are declared.
+namespace {
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void** comm, int nranks, UniqueId id, int rank) = nullptr;
+  int (*Broadcast)(const void* send, void* recv, size_t count, int dtype, int root, void* comm, cudaStream_t st) = nullptr;
+  int (*CommDestroy)(void* comm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.Broadcast && api.CommDestroy;
+  });
+  return api;
+}
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    NcclApi& a = nccl();
+    throw Error(std::string(what) + " failed: " + (a.GetErrorString ? a.GetErrorString(rc) : "nccl error " + std::to_string(rc)));
+  }
+}
+}  // namespace
+
 extern "C" {
 
-const char* sdb_version(void) { return "sdb200 0.1.0 sm_100a"; }
+const char* sdb_version(void) { return "sdb200 0.2.0 sm_100a"; }
 
 int sdb_create(int device, sdb_ctx** out) {
   if (!out) {
@@ -71,21 +125,13 @@ int sdb_create(int device, sdb_ctx** out) {
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
-    delete h;
+    ctx_teardown(h);  // arenas, stream, model, tickets: nothing of a half-built context may leak
     return 1;
   }
 }
 
 int sdb_destroy(sdb_ctx* ctx) {
-  if (!ctx) return 0;
-  cudaSetDevice(ctx->c.device);
-  cudaDeviceSynchronize();
-  model_destroy(ctx->c);
-  ctx->c.master.destroy();
-  ctx->c.packed.destroy();
-  ctx->c.work.destroy();
-  if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
-  delete ctx;
+  ctx_teardown(ctx);
   return 0;
 }
 
@@ -165,6 +211,66 @@ int sdb_weight_arena(sdb_ctx* ctx, void** dev_ptr, size_t* bytes) {
   API_END
 }
 
+int sdb_nccl_unique_id(void* id128) {
+  try {
+    SDB_CHECK(id128, "null argument");
+    SDB_CHECK(nccl().ok, "libnccl.so.2 not found: multi-GPU weight broadcast unavailable");
+    NcclApi::UniqueId id;
+    nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, sizeof(id));
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+int sdb_broadcast_weights(sdb_ctx* ctx, const void* id128, int rank, int world) {
+  API_BEGIN(ctx)
+  SDB_CHECK(id128 && world >= 1 && rank >= 0 && rank < world, "broadcast_weights arguments");
+  if (world > 1) {
+    SDB_CHECK(nccl().ok, "libnccl.so.2 not found: multi-GPU weight broadcast unavailable");
+    NcclApi::UniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    nccl_check(nccl().CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    try {
+      // (1) the fp32 master arena: every tensor of the registry in one contiguous block (dtype 7 = ncclFloat32)
+      nccl_check(nccl().Broadcast(c.master.base, c.master.base, c.master.off / sizeof(float), 7, 0, comm, c.stream), "ncclBroadcast(arena)");
+      // (2) the per-norm eps table a dump-dir carries beside the tensors (host map on rank 0): one float per registry tensor
+      // (0 = default), so ranks that did not read the directory normalise with the same eps
+      const size_t nt = c.tensors.size();
+      std::vector<float> eps(nt, 0.f);
+      if (rank == 0)
+        for (size_t i = 0; i < nt; ++i)
+          if (c.tensors[i].kind == K_NORM_G) {
+            const std::string& nm = c.tensors[i].name;
+            auto it = c.norm_eps.find(nm.substr(0, nm.rfind('/')));
+            if (it != c.norm_eps.end()) eps[i] = it->second;
+          }
+      float* d_eps = (float*)c.io(5, nt * sizeof(float));
+      SDB_CUDA(cudaMemcpyAsync(d_eps, eps.data(), nt * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+      nccl_check(nccl().Broadcast(d_eps, d_eps, nt, 7, 0, comm, c.stream), "ncclBroadcast(eps)");
+      SDB_CUDA(cudaMemcpyAsync(eps.data(), d_eps, nt * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      SDB_CUDA(cudaStreamSynchronize(c.stream));
+      if (rank != 0) {
+        c.norm_eps.clear();
+        for (size_t i = 0; i < nt; ++i)
+          if (eps[i] > 0.f) {
+            const std::string& nm = c.tensors[i].name;
+            c.norm_eps[nm.substr(0, nm.rfind('/'))] = eps[i];
+          }
+      }
+    } catch (...) {
+      nccl().CommDestroy(comm);
+      throw;
+    }
+    nccl_check(nccl().CommDestroy(comm), "ncclCommDestroy");
+  }
+  c.finalized = false;
+  API_END
+}
+
 int sdb_finalize_weights(sdb_ctx* ctx) {
   API_BEGIN(ctx)
   model_finalize(c);
@@ -236,6 +342,25 @@ int sdb_sample_image_dev(sdb_ctx* ctx, const float* d_context, int n, int L, con
   need_final(c);
   model_sample_dev(c, d_context, n, L, d_uncond, Lu, guidance_scale, n_steps, d_init_latent, H, W, nullptr, d_rgb,
                    (cudaStream_t)stream);
+  API_END
+}
+
+int sdb_forward_diffuser(sdb_ctx* ctx, const float* latent, int32_t timestep, const float* context, int n, int L,
+                         const float* uncond, int Lu, double guidance_scale, int H, int W, float* pred, float* out_uncond,
+                         float* out_cond) {
+  API_BEGIN(ctx)
+  need_final(c);
+  SDB_CHECK(latent && context && uncond, "null argument");
+  model_forward_diffuser_host(c, latent, timestep, context, n, L, uncond, Lu, guidance_scale, H, W, pred, out_uncond, out_cond);
+  API_END
+}
+
+int sdb_forward_diffuser_dev(sdb_ctx* ctx, const float* d_latent, int32_t timestep, const float* d_context, int n, int L,
+                             const float* d_uncond, int Lu, double guidance_scale, int H, int W, float* d_pred, void* stream) {
+  API_BEGIN(ctx)
+  need_final(c);
+  model_forward_diffuser_dev(c, d_latent, timestep, d_context, n, L, d_uncond, Lu, guidance_scale, H, W, d_pred, nullptr, nullptr,
+                             (cudaStream_t)stream);
   API_END
 }
 
@@ -355,6 +480,70 @@ int sdb_test_linear(sdb_ctx* ctx, const float* a, const float* w, const float* b
   run_gemm(c, G_LINEAR, A, nullptr, Wp, passes, ep);
   SDB_CUDA(cudaMemcpyAsync(out, d_c, sizeof(float) * M * N, cudaMemcpyDeviceToHost, c.stream));
   SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_gemm_ex(sdb_ctx* ctx, const float* a, const float* w, const float* bias, const float* residual, int M, int K, int N,
+                     int passes, int flags, const float* xa, const float* xw, int XK, float* out) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  const bool geglu = flags & 1, from_f16 = flags & 4;
+  SDB_CHECK(!geglu || (N % 128 == 0 && !residual && !xa), "GEGLU test: N (= 2 * hidden) must be a multiple of 128, no residual / extra K");
+  const int Nout = geglu ? N / 2 : N;
+  auto up = [&](const float* h, size_t cnt) {
+    float* d = c.work.get<float>(cnt);
+    SDB_CUDA(cudaMemcpyAsync(d, h, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
+    return d;
+  };
+  float* d_a = up(a, (size_t)M * K);
+  float* d_w = up(w, (size_t)K * N);
+  float* d_b = bias ? up(bias, N) : nullptr;
+  float* d_r = residual ? up(residual, (size_t)M * N) : nullptr;
+  float* d_c = c.work.get<float>((size_t)M * Nout);
+  ActOp A;
+  A.p = Half2Ptr{c.work.get<__half>((size_t)M * K), c.work.get<__half>((size_t)M * K)};
+  A.W = M, A.C = K;
+  convert_f16_launch(d_a, (long long)M * K, A.p, c.stream);
+  WeightOp Wp;
+  Wp.p = Half2Ptr{c.work.get<__half>((size_t)N * K), c.work.get<__half>((size_t)N * K)};
+  Wp.N = N, Wp.K = K;
+  float* d_bp = d_b;
+  if (geglu) {
+    SDB_CHECK(bias, "GEGLU test needs a bias");
+    d_bp = c.work.get<float>(N);
+    pack_geglu_launch(d_w, d_b, K, N / 2, 64, Wp.p, d_bp, c.stream);
+  } else {
+    pack_linear_launch(d_w, K, N, Wp.p, 0, c.stream);
+  }
+  ExtraK xk;
+  if (xa) {
+    SDB_CHECK(xw && XK % 64 == 0, "extra-K test operands");
+    float* d_xa = up(xa, (size_t)M * XK);
+    float* d_xw = up(xw, (size_t)XK * N);
+    xk.x0.p = Half2Ptr{c.work.get<__half>((size_t)M * XK), c.work.get<__half>((size_t)M * XK)};
+    xk.x0.W = M, xk.x0.C = XK;
+    convert_f16_launch(d_xa, (long long)M * XK, xk.x0.p, c.stream);
+    xk.w.p = Half2Ptr{c.work.get<__half>((size_t)N * XK), c.work.get<__half>((size_t)N * XK)};
+    xk.w.N = N, xk.w.K = XK;
+    pack_linear_launch(d_xw, XK, N, xk.w.p, 0, c.stream);
+  }
+  Epilogue ep;
+  Half2Ptr o16;
+  if (geglu || from_f16) o16 = Half2Ptr{c.work.get<__half>((size_t)M * Nout), c.work.get<__half>((size_t)M * Nout)};
+  ep.out_f32 = geglu ? nullptr : d_c;
+  ep.out_f16 = o16;
+  ep.bias = d_bp, ep.residual = d_r, ep.geglu = geglu ? 1 : 0;
+  run_gemm(c, G_LINEAR, A, nullptr, Wp, passes, ep, xa ? &xk : nullptr);
+  if (geglu || from_f16) {
+    std::vector<__half> hi((size_t)M * Nout), lo((size_t)M * Nout);
+    SDB_CUDA(cudaMemcpyAsync(hi.data(), o16.hi, hi.size() * 2, cudaMemcpyDeviceToHost, c.stream));
+    SDB_CUDA(cudaMemcpyAsync(lo.data(), o16.lo, lo.size() * 2, cudaMemcpyDeviceToHost, c.stream));
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+    for (size_t i = 0; i < hi.size(); ++i) out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+  } else {
+    SDB_CUDA(cudaMemcpyAsync(out, d_c, sizeof(float) * M * Nout, cudaMemcpyDeviceToHost, c.stream));
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+  }
   API_END
 }
 

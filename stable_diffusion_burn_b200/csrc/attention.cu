@@ -101,7 +101,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  const int kvlen = p.kvlen ? p.kvlen[s] : p.Nk;
+  // a device-side length of 0 (or beyond Nk) would leave T = 0 and the epilogue waiting forever: clamp to [1, Nk]
+  const int kvlen = p.kvlen ? max(1, min(p.kvlen[s], p.Nk)) : p.Nk;
   const int T = (kvlen + 127) / 128;
   // columns: S_g at g*128 ; O_g at NG*128 + g*DPAD
 
@@ -309,11 +310,9 @@ template <int DPAD, int NG>
 static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
                         cudaStream_t st) {
   constexpr int smem = AttnCfg<DPAD, NG>::SMEM;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  if (once.first())
     SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
   launch_k(attention_kernel<DPAD, NG>, grid, dim3(64 + 128 * NG), (size_t)smem, st, mq, mk, mv, p);
 }

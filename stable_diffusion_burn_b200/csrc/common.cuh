@@ -32,6 +32,20 @@ struct Error : std::runtime_error {
                          __FILE__ + ":" + std::to_string(__LINE__));                    \
   } while (0)
 
+// --------------------------------------------------------------------------- per-device one-time setup
+// cudaFuncSetAttribute is per device: a host that opens contexts on several GPUs from one process must set it on each.
+// Usage: static DeviceOnce once; if (once.first()) cudaFuncSetAttribute(...);
+struct DeviceOnce {
+  unsigned long long done = 0;  // bit d: attribute already set on device d (64 devices are plenty for one node)
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    const unsigned long long old = __atomic_fetch_or(&done, bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0;
+  }
+};
+
 // --------------------------------------------------------------------------- launches
 // Programmatic dependent launch (PDL): a kernel launched with the attribute may start (launch latency, CTA
 // scheduling, its prologue up to pdl_wait()) while its predecessor on the stream is still draining.

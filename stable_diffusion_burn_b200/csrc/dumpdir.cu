@@ -108,6 +108,10 @@ void model_load_dump_dir(Ctx& c, const char* root_c) {
     want.insert(want.end(), m.values.begin(), m.values.end());
     SDB_CHECK(p == want, file + ": value differs from the compiled SD-v1.4 topology");
   }
+  // from here on the master arena is overwritten tensor by tensor: a failure midway must not leave the context "finalized"
+  // on stale packed weights
+  c.finalized = false;
+  model_invalidate_graphs(c);
   c.norm_eps.clear();
   std::vector<float> fill;
   for (const TensorInfo& t : c.tensors) {

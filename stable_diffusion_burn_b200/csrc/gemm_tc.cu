@@ -514,11 +514,9 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   constexpr int smem = STAGES * StageLayout<BN, PASSES, CG>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
   constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();
   static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 2 * EW * 32 * 144, "epilogue staging tiles must fit in the stages");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first())
     SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = dim3(64 + 32 * EW), cfg.dynamicSmemBytes = smem, cfg.stream = stream;

@@ -73,6 +73,8 @@ void embed_tokens_launch(const int* tok, const float* E, const float* Pos, int n
 // latent holds 2*count floats: the update is written to both halves (uncond | cond inputs of the next step)
 void cfg_ddim_launch(const float* eps_u, const float* eps_c, float* latent, long long count, float scale,
                      float sqrt_one_minus_at, float sqrt_at, float sqrt_aprev, float dir_coef, cudaStream_t st);
+// pred = u + (c - u) * scale alone (forward_diffuser without the DDIM update)
+void cfg_combine_launch(const float* eps_u, const float* eps_c, long long count, float scale, float* pred, cudaStream_t st);
 // u8 = trunc(clamp((img+1)/2*255, 0, 255)), NCHW fp32 -> NHWC u8 (reference stablediffusion/mod.rs:79-97)
 void to_rgb8_launch(const float* img_nchw, int n, int H, int W, uint8_t* rgb, cudaStream_t st);
 void quant_conv_slice_launch(const float* x, const float* w, const float* b, int n, int HW, float* y, cudaStream_t st);
@@ -100,5 +102,11 @@ void pack_small_cout_launch(const float* w, int Cout, int Cin, float* out, cudaS
 
 // ---- synthetic weights (bit-identical to stable_diffusion_burn_b200/synth.py)
 void synth_fill_launch(float* dst, long long count, uint32_t key, float bound, float offset, cudaStream_t st);
+struct SynthDesc {
+  long long offset, count, chunk0;  // float offset in the arena, element count, index of the tensor's first 64K-element chunk
+  uint32_t key;
+  float bound, shift;
+};
+void synth_fill_table_launch(float* base, const SynthDesc* d_desc, int ntensors, long long nchunks, cudaStream_t st);
 
 }  // namespace sdb

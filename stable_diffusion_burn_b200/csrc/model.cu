@@ -222,6 +222,9 @@ void model_finalize(Ctx& c) {
   m.alphas_host.resize(1000);
   SDB_CUDA(cudaMemcpyAsync(m.alphas_host.data(), mptr(c, m.alphas_i), 4000, cudaMemcpyDeviceToHost, c.stream));
   SDB_CUDA(cudaStreamSynchronize(c.stream));
+  // a context filled through sdb_set_tensor without the schedule tensor would divide by sqrt(0) in every DDIM step
+  for (float a : m.alphas_host)
+    SDB_CHECK(a > 0.f && a <= 1.f, "alpha_cumulative_products must lie in (0, 1]: set the schedule tensor before sdb_finalize_weights");
 }
 
 void model_invalidate_graphs(Ctx& c) {
@@ -894,21 +897,14 @@ void model_unet_forward_dev(Ctx& c, const float* d_x, int t, const float* d_cont
 
 void model_unet_forward_host(Ctx& c, const float* x, int t, const float* context, int n, int H, int W, int L, float* out) {
   const size_t xe = (size_t)n * 4 * H * W, ce = (size_t)n * L * 768;
-  float *d_x, *d_c, *d_o;
-  SDB_CUDA(cudaMalloc(&d_x, xe * 4));
-  SDB_CUDA(cudaMalloc(&d_c, ce * 4));
-  SDB_CUDA(cudaMalloc(&d_o, xe * 4));
-  try {
-    SDB_CUDA(cudaMemcpyAsync(d_x, x, xe * 4, cudaMemcpyHostToDevice, c.stream));
-    SDB_CUDA(cudaMemcpyAsync(d_c, context, ce * 4, cudaMemcpyHostToDevice, c.stream));
-    model_unet_forward_dev(c, d_x, t, d_c, n, H, W, L, d_o, c.stream);
-    SDB_CUDA(cudaMemcpyAsync(out, d_o, xe * 4, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    cudaFree(d_x), cudaFree(d_c), cudaFree(d_o);
-    throw;
-  }
-  cudaFree(d_x), cudaFree(d_c), cudaFree(d_o);
+  float* d_x = (float*)c.io(0, xe * 4);
+  float* d_c = (float*)c.io(1, ce * 4);
+  float* d_o = (float*)c.io(2, xe * 4);
+  SDB_CUDA(cudaMemcpyAsync(d_x, x, xe * 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_c, context, ce * 4, cudaMemcpyHostToDevice, c.stream));
+  model_unet_forward_dev(c, d_x, t, d_c, n, H, W, L, d_o, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(out, d_o, xe * 4, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 static void decode_chunked(Ctx& c, const float* d_latent, int n, int H, int W, float pre_scale, float* d_img) {
@@ -929,19 +925,12 @@ void model_decode_dev(Ctx& c, const float* d_latent, int n, int H, int W, float*
 
 void model_decode_host(Ctx& c, const float* latent, int n, int H, int W, float* img) {
   const size_t le = (size_t)n * 4 * H * W, ie = (size_t)n * 3 * 64 * H * W;
-  float *d_l, *d_i;
-  SDB_CUDA(cudaMalloc(&d_l, le * 4));
-  SDB_CUDA(cudaMalloc(&d_i, ie * 4));
-  try {
-    SDB_CUDA(cudaMemcpyAsync(d_l, latent, le * 4, cudaMemcpyHostToDevice, c.stream));
-    model_decode_dev(c, d_l, n, H, W, d_i, c.stream);
-    SDB_CUDA(cudaMemcpyAsync(img, d_i, ie * 4, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    cudaFree(d_l), cudaFree(d_i);
-    throw;
-  }
-  cudaFree(d_l), cudaFree(d_i);
+  float* d_l = (float*)c.io(0, le * 4);
+  float* d_i = (float*)c.io(1, ie * 4);
+  SDB_CUDA(cudaMemcpyAsync(d_l, latent, le * 4, cudaMemcpyHostToDevice, c.stream));
+  model_decode_dev(c, d_l, n, H, W, d_i, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(img, d_i, ie * 4, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 void model_encode_dev(Ctx& c, const float* d_img, int n, int H, int W, float* d_latent, cudaStream_t caller) {
@@ -965,19 +954,12 @@ void model_encode_dev(Ctx& c, const float* d_img, int n, int H, int W, float* d_
 
 void model_encode_host(Ctx& c, const float* img, int n, int H, int W, float* latent) {
   const size_t ie = (size_t)n * 3 * H * W, le = (size_t)n * 4 * (H / 8) * (W / 8);
-  float *d_i = nullptr, *d_l = nullptr;
-  try {
-    SDB_CUDA(cudaMalloc(&d_i, ie * 4));
-    SDB_CUDA(cudaMalloc(&d_l, le * 4));
-    SDB_CUDA(cudaMemcpyAsync(d_i, img, ie * 4, cudaMemcpyHostToDevice, c.stream));
-    model_encode_dev(c, d_i, n, H, W, d_l, c.stream);
-    SDB_CUDA(cudaMemcpyAsync(latent, d_l, le * 4, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    cudaFree(d_i), cudaFree(d_l);
-    throw;
-  }
-  cudaFree(d_i), cudaFree(d_l);
+  float* d_i = (float*)c.io(0, ie * 4);
+  float* d_l = (float*)c.io(1, le * 4);
+  SDB_CUDA(cudaMemcpyAsync(d_i, img, ie * 4, cudaMemcpyHostToDevice, c.stream));
+  model_encode_dev(c, d_i, n, H, W, d_l, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(latent, d_l, le * 4, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // latent_to_image (stablediffusion/mod.rs:69-100)
@@ -991,21 +973,13 @@ static void latent_to_image_dev(Ctx& c, const float* d_latent, int n, int H, int
 
 void model_latent_to_image_host(Ctx& c, const float* latent, int n, int H, int W, uint8_t* rgb) {
   const size_t le = (size_t)n * 4 * H * W, re = (size_t)n * 3 * 64 * H * W;
-  float* d_l;
-  uint8_t* d_r;
-  SDB_CUDA(cudaMalloc(&d_l, le * 4));
-  SDB_CUDA(cudaMalloc(&d_r, re));
-  try {
-    c.work.reset();
-    SDB_CUDA(cudaMemcpyAsync(d_l, latent, le * 4, cudaMemcpyHostToDevice, c.stream));
-    latent_to_image_dev(c, d_l, n, H, W, d_r);
-    SDB_CUDA(cudaMemcpyAsync(rgb, d_r, re, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    cudaFree(d_l), cudaFree(d_r);
-    throw;
-  }
-  cudaFree(d_l), cudaFree(d_r);
+  float* d_l = (float*)c.io(0, le * 4);
+  uint8_t* d_r = (uint8_t*)c.io(1, re);
+  c.work.reset();
+  SDB_CUDA(cudaMemcpyAsync(d_l, latent, le * 4, cudaMemcpyHostToDevice, c.stream));
+  latent_to_image_dev(c, d_l, n, H, W, d_r);
+  SDB_CUDA(cudaMemcpyAsync(rgb, d_r, re, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // sample_latent + latent_to_image (stablediffusion/mod.rs:51-160). The conditional and unconditional UNet
@@ -1114,30 +1088,75 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
 void model_sample_host(Ctx& c, const float* context, int n, int L, const float* uncond, int Lu, double scale, int n_steps,
                        const float* init_latent, uint64_t seed, int H, int W, float* latent_out, uint8_t* rgb) {
   const size_t le = (size_t)n * 4 * H * W, ce = (size_t)n * L * 768, ue = (size_t)Lu * 768, re = (size_t)n * 3 * 64 * H * W;
-  float *d_c = nullptr, *d_u = nullptr, *d_l = nullptr, *d_lo = nullptr;
-  uint8_t* d_r = nullptr;
-  auto free_all = [&] { cudaFree(d_c), cudaFree(d_u), cudaFree(d_l), cudaFree(d_lo), cudaFree(d_r); };
-  try {
-    SDB_CUDA(cudaMalloc(&d_c, ce * 4));
-    SDB_CUDA(cudaMalloc(&d_u, ue * 4));
-    SDB_CUDA(cudaMalloc(&d_l, le * 4));
-    if (latent_out) SDB_CUDA(cudaMalloc(&d_lo, le * 4));
-    if (rgb) SDB_CUDA(cudaMalloc(&d_r, re));
-    SDB_CUDA(cudaMemcpyAsync(d_c, context, ce * 4, cudaMemcpyHostToDevice, c.stream));
-    SDB_CUDA(cudaMemcpyAsync(d_u, uncond, ue * 4, cudaMemcpyHostToDevice, c.stream));
-    if (init_latent)
-      SDB_CUDA(cudaMemcpyAsync(d_l, init_latent, le * 4, cudaMemcpyHostToDevice, c.stream));
-    else
-      randn_launch(d_l, (long long)le, seed, c.stream);
-    model_sample_dev(c, d_c, n, L, d_u, Lu, scale, n_steps, d_l, H, W, d_lo, d_r, c.stream);
-    if (latent_out) SDB_CUDA(cudaMemcpyAsync(latent_out, d_lo, le * 4, cudaMemcpyDeviceToHost, c.stream));
-    if (rgb) SDB_CUDA(cudaMemcpyAsync(rgb, d_r, re, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    free_all();
-    throw;
+  float* d_c = (float*)c.io(0, ce * 4);
+  float* d_u = (float*)c.io(1, ue * 4);
+  float* d_l = (float*)c.io(2, le * 4);
+  float* d_lo = latent_out ? (float*)c.io(3, le * 4) : nullptr;
+  uint8_t* d_r = rgb ? (uint8_t*)c.io(4, re) : nullptr;
+  SDB_CUDA(cudaMemcpyAsync(d_c, context, ce * 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_u, uncond, ue * 4, cudaMemcpyHostToDevice, c.stream));
+  if (init_latent)
+    SDB_CUDA(cudaMemcpyAsync(d_l, init_latent, le * 4, cudaMemcpyHostToDevice, c.stream));
+  else
+    randn_launch(d_l, (long long)le, seed, c.stream);
+  model_sample_dev(c, d_c, n, L, d_u, Lu, scale, n_steps, d_l, H, W, d_lo, d_r, c.stream);
+  if (latent_out) SDB_CUDA(cudaMemcpyAsync(latent_out, d_lo, le * 4, cudaMemcpyDeviceToHost, c.stream));
+  if (rgb) SDB_CUDA(cudaMemcpyAsync(rgb, d_r, re, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// forward_diffuser (stablediffusion/mod.rs:162-192): the two UNet evaluations of one guidance step as ONE batch-2n pass (the
+// same pass sample_latent replays as a CUDA graph), then pred = u + (c - u) * scale. d_u / d_c may be null.
+void model_forward_diffuser_dev(Ctx& c, const float* d_latent, int t, const float* d_context, int n, int L, const float* d_uncond,
+                                int Lu, double scale, int H, int W, float* d_pred, float* d_u, float* d_c, cudaStream_t caller) {
+  SDB_CHECK(n >= 1 && L >= 1 && Lu >= 1 && t >= 0 && t < 1000, "forward_diffuser arguments");
+  SDB_CHECK(H % 8 == 0 && W % 8 == 0 && ((H / 8) * (W / 8)) % 8 == 0, "unsupported latent size");
+  StreamJoin join(c, caller);
+  c.work.reset();
+  const int nb = 2 * n;
+  const int Lpad = round_up(std::max(L, Lu), 32);
+  const size_t le = (size_t)n * 4 * H * W;
+  float* ctxp = c.work.get<float>((size_t)nb * Lpad * 768);
+  float* xb = c.work.get<float>(2 * le);
+  float* eps = c.work.get<float>(2 * le);
+  int* d_t = c.work.get<int>(1);
+  int* d_len = c.work.get<int>(nb);
+  SDB_CUDA(cudaMemsetAsync(ctxp, 0, (size_t)nb * Lpad * 768 * 4, c.stream));
+  for (int i = 0; i < n; ++i)
+    SDB_CUDA(cudaMemcpyAsync(ctxp + (size_t)i * Lpad * 768, d_uncond, (size_t)Lu * 768 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  SDB_CUDA(cudaMemcpy2DAsync(ctxp + (size_t)n * Lpad * 768, (size_t)Lpad * 768 * 4, d_context, (size_t)L * 768 * 4,
+                             (size_t)L * 768 * 4, n, cudaMemcpyDeviceToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(xb, d_latent, le * 4, cudaMemcpyDeviceToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(xb + le, d_latent, le * 4, cudaMemcpyDeviceToDevice, c.stream));
+  std::vector<int> lens(nb);
+  for (int i = 0; i < nb; ++i) lens[i] = i < n ? Lu : L;
+  SDB_CUDA(cudaMemcpyAsync(d_t, &t, 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_len, lens.data(), nb * 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  unet_pass(c, nb, xb, d_t, ctxp, Lpad, d_len, H, W, eps, nullptr);
+  if (d_u) SDB_CUDA(cudaMemcpyAsync(d_u, eps, le * 4, cudaMemcpyDeviceToDevice, c.stream));
+  if (d_c) SDB_CUDA(cudaMemcpyAsync(d_c, eps + le, le * 4, cudaMemcpyDeviceToDevice, c.stream));
+  if (d_pred) {
+    KernelScope ks(c, KC_ELEMENTWISE);
+    cfg_combine_launch(eps, eps + le, (long long)le, (float)scale, d_pred, c.stream);
   }
-  free_all();
+}
+
+void model_forward_diffuser_host(Ctx& c, const float* latent, int t, const float* context, int n, int L, const float* uncond,
+                                 int Lu, double scale, int H, int W, float* pred, float* out_u, float* out_c) {
+  const size_t le = (size_t)n * 4 * H * W, ce = (size_t)n * L * 768, ue = (size_t)Lu * 768;
+  float* d_l = (float*)c.io(0, le * 4);
+  float* d_c = (float*)c.io(1, ce * 4);
+  float* d_u = (float*)c.io(2, ue * 4);
+  float* d_o = (float*)c.io(3, 3 * le * 4);
+  SDB_CUDA(cudaMemcpyAsync(d_l, latent, le * 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_c, context, ce * 4, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(d_u, uncond, ue * 4, cudaMemcpyHostToDevice, c.stream));
+  model_forward_diffuser_dev(c, d_l, t, d_c, n, L, d_u, Lu, scale, H, W, d_o, d_o + le, d_o + 2 * le, c.stream);
+  if (pred) SDB_CUDA(cudaMemcpyAsync(pred, d_o, le * 4, cudaMemcpyDeviceToHost, c.stream));
+  if (out_u) SDB_CUDA(cudaMemcpyAsync(out_u, d_o + le, le * 4, cudaMemcpyDeviceToHost, c.stream));
+  if (out_c) SDB_CUDA(cudaMemcpyAsync(out_c, d_o + 2 * le, le * 4, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // ================================================================================ CLIP text encoder
@@ -1220,20 +1239,12 @@ void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out
   // which cannot see the ids without a sync, clamps instead)
   for (long long i = 0; i < (long long)n * L; ++i)
     SDB_CHECK(tokens[i] >= 0 && tokens[i] < 49408, "clip_forward: token id outside the 49408-entry vocabulary");
-  int* d_t = nullptr;
-  float* d_o = nullptr;
-  try {
-    SDB_CUDA(cudaMalloc(&d_t, (size_t)n * L * 4));
-    SDB_CUDA(cudaMalloc(&d_o, (size_t)n * L * 768 * 4));
-    SDB_CUDA(cudaMemcpyAsync(d_t, tokens, (size_t)n * L * 4, cudaMemcpyHostToDevice, c.stream));
-    model_clip_forward_dev(c, d_t, n, L, d_o, c.stream);
-    SDB_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * L * 768 * 4, cudaMemcpyDeviceToHost, c.stream));
-    SDB_CUDA(cudaStreamSynchronize(c.stream));
-  } catch (...) {
-    cudaFree(d_t), cudaFree(d_o);
-    throw;
-  }
-  cudaFree(d_t), cudaFree(d_o);
+  int* d_t = (int*)c.io(0, (size_t)n * L * 4);
+  float* d_o = (float*)c.io(1, (size_t)n * L * 768 * 4);
+  SDB_CUDA(cudaMemcpyAsync(d_t, tokens, (size_t)n * L * 4, cudaMemcpyHostToDevice, c.stream));
+  model_clip_forward_dev(c, d_t, n, L, d_o, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * L * 768 * 4, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // ================================================================================ attention unit-test entry

@@ -23,6 +23,10 @@ void model_sample_host(Ctx& c, const float* context, int n, int L, const float* 
 void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float* d_uncond, int Lu, double scale,
                       int n_steps, const float* d_init_latent, int H, int W, float* d_latent_out, uint8_t* d_rgb,
                       cudaStream_t caller);
+void model_forward_diffuser_dev(Ctx& c, const float* d_latent, int t, const float* d_context, int n, int L, const float* d_uncond,
+                                int Lu, double scale, int H, int W, float* d_pred, float* d_u, float* d_c, cudaStream_t caller);
+void model_forward_diffuser_host(Ctx& c, const float* latent, int t, const float* context, int n, int L, const float* uncond,
+                                 int Lu, double scale, int H, int W, float* pred, float* out_u, float* out_c);
 void model_clip_forward_dev(Ctx& c, const int* d_tokens, int n, int L, float* d_out, cudaStream_t caller);
 void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out);
 // dump-dir reader (dumpdir.cu)

@@ -302,6 +302,8 @@ static uint32_t mix32_host(uint32_t x) {
 void model_init_synthetic(Ctx& c, uint32_t seed) {
   auto* m = reinterpret_cast<Model*>(c.model);
   float* base = reinterpret_cast<float*>(c.master.base);
+  std::vector<SynthDesc> table;
+  long long nchunks = 0;
   for (const TensorInfo& t : c.tensors) {
     if (t.kind == K_SCHED) continue;
     float bound = 0.f, offset = 0.f;
@@ -325,7 +327,14 @@ void model_init_synthetic(Ctx& c, uint32_t seed) {
         break;
     }
     const uint32_t key = mix32_host(fnv1a32(t.name) + seed);
-    synth_fill_launch(base + t.offset, t.count, key, bound, offset, c.stream);
+    table.push_back(SynthDesc{(long long)t.offset, (long long)t.count, nchunks, key, bound, offset});
+    nchunks += (t.count + 65535) / 65536;
+  }
+  {  // one launch for the whole registry; the descriptor table is staged through the work arena
+    c.work.reset();
+    SynthDesc* d_table = c.work.get<SynthDesc>(table.size());
+    SDB_CUDA(cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(SynthDesc), cudaMemcpyHostToDevice, c.stream));
+    synth_fill_table_launch(base, d_table, (int)table.size(), nchunks, c.stream);
   }
   // SD-v1 scaled-linear schedule (synth.alpha_cumulative_products)
   std::vector<float> a(1000);

@@ -34,6 +34,25 @@ void* Arena::alloc(size_t bytes) {
   return base + a;
 }
 
+void* Ctx::io(int slot, size_t bytes) {
+  IoBuf& b = iobuf[slot];
+  if (bytes > b.cap) {
+    SDB_CUDA(cudaStreamSynchronize(stream));  // nothing queued may still read the old buffer
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr, b.cap = 0;
+    const size_t want = (bytes + (1u << 20) - 1) & ~size_t((1u << 20) - 1);
+    SDB_CUDA(cudaMalloc(&b.p, want));
+    b.cap = want;
+  }
+  return b.p;
+}
+void Ctx::io_destroy() {
+  for (IoBuf& b : iobuf) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr, b.cap = 0;
+  }
+}
+
 float* Ctx::master_ptr(const std::string& name) {
   auto it = index.find(name);
   if (it == index.end()) throw Error("unknown tensor: " + name);
@@ -155,6 +174,9 @@ static CUtensorMap make_mat_map(const __half* ptr, long long ld, long long rows,
 
 void run_attention(Ctx& c, const AttnOp& a) {
   SDB_CHECK(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0, "attention leading dims must be multiples of 8");
+  // the causal mask is applied inside the first key tile only (CLIP: L <= 77); longer causal sequences are not supported
+  SDB_CHECK(!a.causal || a.Nk <= 128, "causal attention supports at most 128 keys");
+  SDB_CHECK(a.Nk >= 1 && a.Nq >= 1, "attention needs at least one query and one key");
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.nb = a.nb, p.heads = a.heads, p.d = a.d, p.dpad = a.dpad, p.Nq = a.Nq, p.Nk = a.Nk;

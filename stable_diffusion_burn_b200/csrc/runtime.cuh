@@ -118,6 +118,13 @@ struct Ctx {
   int64_t launches = 0;
   double cls_ms[KC_COUNT] = {0}, cls_flops[KC_COUNT] = {0}, cls_bytes[KC_COUNT] = {0};
   int64_t cls_launches[KC_COUNT] = {0};
+  // grow-only device staging for the host-buffer entry points (no cudaMalloc/cudaFree per call: each is a device-wide sync)
+  struct IoBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+  } iobuf[6];
+  void* io(int slot, size_t bytes);
+  void io_destroy();
   void* model = nullptr;  // Model* (model.cu)
   unsigned int* splitk_tickets = nullptr;  // 64K zeroed counters (gemm_tc split-K tile tickets)
   // SDB_DEBUG_SYNC=1: synchronise after every launch and report the failing op (bring-up aid)

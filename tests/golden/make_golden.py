@@ -1,8 +1,7 @@
 """Generates tests/golden/*.npz from the CPU oracle (oracle/sd_oracle.py) on the synthetic weights (seed 0).
 
-The reference has no golden vectors for this path and cannot run here (see oracle header: PARITY UNPINNED),
-so these fixtures pin the ORACLE: the CPU suite re-derives a subset and the GPU suite compares the CUDA path
-against them. Run from the repo root:  python tests/golden/make_golden.py
+The oracle itself is pinned against the reference's own Python model (tests/test_ref_pin_cpu.py, tests/ref_shim/); these
+fixtures are what the GPU suite holds the CUDA path to (erf GELU, like the Rust model), and the CPU suite re-derives a subset. Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -67,9 +66,70 @@ def enc_golden():
     np.savez_compressed(os.path.join(OUT, "vae_enc.npz"), **keep)
 
 
+def round2_cases(P):
+    """Fixtures for the configurations bench.py actually times: the CFG batch at L = 77 / Lu = 2, 20 DDIM
+    steps, batch 8 at 64x64 (C3/C5), the 96x96 -> 768x768 decode (C4). Select with `make_golden.py r2` (or one of the names)."""
+    sel = lambda name: (not ONLY) or ("r2" in ONLY) or (name in ONLY)
+    unc = torch.from_numpy(synth.make_context(1, 2, seed=99))[0]
+    with torch.no_grad():
+        if sel("cfg_L77"):
+            # forward_diffuser on the bench's exact shape: n = 1, 64x64, L = 77, Lu = 2, t = 999 and a mid-schedule t
+            keep = {}
+            x = torch.from_numpy(synth.make_latent(1, 64, 64))
+            ctx = torch.from_numpy(synth.make_context(1, 77))
+            for t in (999, 449):
+                taps = {}
+                t1 = time.time()
+                pred = O.forward_diffuser(P, x, t, ctx, unc, 7.5, taps=taps)
+                keep[f"t{t}:uncond"], keep[f"t{t}:cond"], keep[f"t{t}:pred"] = taps["uncond"].numpy(), taps["cond"].numpy(), pred.numpy()
+                print("cfg_L77", t, time.time() - t1, flush=True)
+            np.savez_compressed(os.path.join(OUT, "cfg_L77.npz"), **keep)
+        if sel("unet_b8_64"):
+            x = torch.from_numpy(synth.make_latent(8, 64, 64, seed=808))
+            ctx = torch.from_numpy(synth.make_context(8, 77, seed=88))
+            t1 = time.time()
+            y = torch.cat([O.unet_forward(P, x[i:i + 1], 599, ctx[i:i + 1]) for i in range(8)])
+            print("unet_b8_64", time.time() - t1, flush=True)
+            np.savez_compressed(os.path.join(OUT, "unet_b8_64.npz"), out=y.numpy())
+        if sel("vae_96"):
+            lat = torch.from_numpy(synth.make_latent(1, 96, 96, seed=96))
+            t1 = time.time()
+            img = O.decode_latent(P, lat)
+            print("vae_96", time.time() - t1, tuple(img.shape), flush=True)
+            np.savez_compressed(os.path.join(OUT, "vae_96.npz"), img_sub=img[:, :, ::8, ::8].numpy().copy(),
+                                img_rows=img[:, :, 380:384, :].numpy().copy(), mean=float(img.mean()), std=float(img.std()))
+        if sel("sample_20step"):
+            # C2 exactly: n = 1, 64x64, 20 steps, cfg 7.5, L = 77, Lu = 2. Taps at steps 0 / 9 / 19: the latent that entered the
+            # step and the two UNet outputs on it (per-step parity is judged on the ORACLE's latent), plus the free-running result.
+            ctx = torch.from_numpy(synth.make_context(1, 77))
+            init = torch.from_numpy(synth.make_latent(1, 64, 64))
+            taps = {}
+            t1 = time.time()
+            lat = O.sample_latent(P, ctx, unc, 7.5, 20, init, taps=taps)
+            print("sample_20step latent", time.time() - t1, flush=True)
+            imgf = O.latent_to_image_f32(P, lat)
+            keep = {"latent": lat.numpy(), "u8_sub": O.to_u8(imgf)[:, ::2, ::2, :].copy(), "img_f32_sub": imgf[:, ::4, ::4, :].numpy().copy()}
+            ts, _ = O.ddim_timesteps(20)
+            for i in (0, 9, 19):
+                keep[f"step{i}:t"] = np.int32(ts[i])
+                for k in ("latent_in", "uncond", "cond", "latent"):
+                    keep[f"step{i}:{k}"] = taps[f"step{i}/{k}"].numpy()
+            keep["latent_rms_per_step"] = np.asarray([float(taps[f"step{i}/latent"].pow(2).mean().sqrt()) for i in range(20)], np.float32)
+            np.savez_compressed(os.path.join(OUT, "sample_20step.npz"), **keep)
+
+
+R2_NAMES = {"r2", "cfg_L77", "unet_b8_64", "vae_96", "sample_20step"}
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
+    if ONLY and ONLY <= R2_NAMES:
+        P = O.Params(synth.make_params(0))
+        print("params", time.time() - t0, flush=True)
+        round2_cases(P)
+        print("done", time.time() - t0)
+        return
     if not ONLY or "enc" in ONLY:
         enc_golden()
         if ONLY == {"enc"}:
@@ -128,6 +188,7 @@ def main():
         print("e2e 1 step", time.time() - t1, flush=True)
         np.savez_compressed(os.path.join(OUT, "sample_1step.npz"), latent=lat1.numpy(), img_f32_sub=imgf[:, ::4, ::4, :].numpy().copy(),
                             u8=u8)
+    round2_cases(P)
     finish(P, t0)
 
 
