@@ -36,12 +36,21 @@ def peaks():
 
 
 def gemm_traffic_per_launch():
-    """DRAM bytes per gemm_tc launch from the committed ncu capture (profiles/r1_gemm_traffic.json), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    """DRAM bytes per gemm_tc launch from the committed ncu capture (profiles/r2_gemm_traffic.json, else round 1's), or None."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
+
+
+def workload_config(args, n):
+    """`config` of the JSON line — identical in both arms (the reference arm runs on this arm's config)."""
+    return {"workload": f"SDv1-4 txt2img {args.size}x{args.size}, {args.ddim_steps} steps, cfg=7.5, batch={n} per GPU",
+            "context_len": args.context_len, "precision_option": args.precision,
+            "l2": "inputs larger than L2: >1.9 GB of packed weights stream from HBM every UNet step (L2 = 126 MB)"}
 
 
 class ClockSampler:
@@ -96,11 +105,10 @@ GF_UNET_64, GF_UNET_32 = 804.4, 178.2
 GF_DEC_64, GF_DEC_32 = 2518.4, 631.6
 
 
-def cpu_port_times(n_steps=1, budget_s=30.0):
-    """Times the CPU port of the reference path (oracle/, torch fp32 on the host cores) on a BOUNDED sample.
-    Probe: one cond UNet eval + one decode on a 32x32 latent. If the probe predicts that a full 64x64 DDIM step
-    (2 UNet evals) fits `budget_s`, the real thing is timed; otherwise the probe is scaled by the FLOP ratio.
-    Returns (seconds per 64x64 DDIM step [list], seconds per 64x64 decode, threads, description)."""
+def cpu_port_times(n_steps=1, latent=64, ddim_steps_total=20):
+    """Times the CPU port of the reference path (oracle/, torch fp32 on the host cores): `n_steps` REAL DDIM steps (cond + uncond
+    UNet at the full latent size, L = 77 / Lu = 2, the timesteps a `ddim_steps_total`-step schedule starts with) and one REAL
+    decode_latent. Nothing is extrapolated. Returns (seconds per DDIM step [list], seconds per decode, threads, description)."""
     import torch
 
     from oracle import sd_oracle as O
@@ -110,33 +118,19 @@ def cpu_port_times(n_steps=1, budget_s=30.0):
     P = O.Params(synth.make_params(0))
     ctx = torch.from_numpy(synth.make_context(1, 77))
     unc = torch.from_numpy(synth.make_context(1, 2, seed=99))[0]
+    ts, _ = O.ddim_timesteps(ddim_steps_total)
     with torch.no_grad():
-        lat32 = torch.from_numpy(synth.make_latent(1, 32, 32))
-        O.unet_forward(P, lat32[:, :, :16, :16].contiguous(), 999, ctx)  # warm-up (thread pool, allocator)
-        t0 = time.perf_counter()
-        O.unet_forward(P, lat32, 999, ctx)
-        t_u32 = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.decode_latent(P, lat32 * (1.0 / 0.18215))
-        t_d32 = time.perf_counter() - t0
-        pred_step = 2 * t_u32 * GF_UNET_64 / GF_UNET_32
-        pred_dec = t_d32 * GF_DEC_64 / GF_DEC_32
-        if n_steps * pred_step + pred_dec <= budget_s:
-            lat = torch.from_numpy(synth.make_latent(1, 64, 64))
-            steps = []
-            for _ in range(n_steps):
-                t0 = time.perf_counter()
-                O.forward_diffuser(P, lat, 999, ctx, unc, 7.5)
-                steps.append(time.perf_counter() - t0)
+        lat = torch.from_numpy(synth.make_latent(1, latent, latent))
+        O.unet_forward(P, lat[:, :, :16, :16].contiguous(), 999, ctx)  # thread pool / allocator warm-up, not a step
+        steps = []
+        for i in range(n_steps):
             t0 = time.perf_counter()
-            O.decode_latent(P, lat * (1.0 / 0.18215))
-            dec = time.perf_counter() - t0
-            what = f"{n_steps} full 64x64 DDIM step(s) (cond+uncond UNet) + 1 decode_latent, timed directly"
-        else:
-            steps = [pred_step] * n_steps
-            dec = pred_dec
-            what = (f"probe on a 32x32 latent (1 UNet eval {t_u32:.2f} s, 1 decode {t_d32:.2f} s) scaled by the algorithmic FLOP ratio "
-                    f"(x{GF_UNET_64 / GF_UNET_32:.2f} per UNet eval, x{GF_DEC_64 / GF_DEC_32:.2f} decode): a full step would exceed the {budget_s:.0f} s budget")
+            O.forward_diffuser(P, lat, ts[i % len(ts)], ctx, unc, 7.5)
+            steps.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        O.decode_latent(P, lat * (1.0 / 0.18215))
+        dec = time.perf_counter() - t0
+    what = f"{n_steps} real {latent}x{latent} DDIM step(s) (cond+uncond UNet, L=77/Lu=2) + 1 real decode_latent, timed directly on {threads} threads"
     return steps, dec, threads, what
 
 
@@ -175,23 +169,26 @@ def gpu_eager_times():
 
 
 def run_reference(args):
-    """Reference arm: the reference's own implementation cannot be built here (Rust, no toolchain), so this times
-    the CPU port. Each bench step = one DDIM step (2 UNet evals) — a bounded sample of the 20-step workload."""
+    """Reference arm: the reference's own implementation cannot be built here (Rust, no toolchain; DESIGN.md §2), so this times
+    the CPU port of the same path on the host cores. A bench "step" of this arm is ONE real DDIM step of the workload (2 UNet
+    evaluations at the full latent size) — a bounded sample of the 20-step image; warm-up and timed steps are all real, and one
+    real decode is timed beside them. value = 1 / (ddim_steps * mean_step + decode)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     total = args.warmup + args.steps
-    step_s, dec, threads, what = cpu_port_times(total, budget_s=150.0)
+    step_s, dec, threads, what = cpu_port_times(total, latent=args.size // 8, ddim_steps_total=args.ddim_steps)
     timed = step_s[args.warmup:]
     mean_step = sum(timed) / len(timed)
-    img_s = 20 * mean_step + dec
+    img_s = args.ddim_steps * mean_step + dec
     value = 1.0 / img_s
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": mean_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SDv1-4 txt2img 512x512, 20 steps, cfg=7.5, batch=1 (CPU port of the Burn path; torch-CPU fp32)",
-                   "note": "each timed step is ONE DDIM step (cond+uncond UNet); value = 1/(20*mean_step + decode)"},
+        "config": workload_config(args, args.batch),
+        "impl_note": "CPU port of the Burn path (oracle/, torch-CPU fp32; the Rust reference cannot be built in this image). Each timed "
+                     "step is ONE real DDIM step (cond+uncond UNet); value = 1/(ddim_steps*mean_step + decode), decode timed once",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{what} ({mean_step:.2f} s/step, decode {dec:.2f} s)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,6 +215,7 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 = per-layer policy (meets 1e-3), 1/2/3 = force passes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="multi-GPU runs: skip the BASELINE configs[4] sub-record (8 images per rank)")
     ap.add_argument("--ref-cuda", action="store_true",
                     help="with --impl reference: also time the torch restatement on cuda:0 (labelled secondary comparator)")
     args = ap.parse_args()
@@ -243,50 +241,52 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from stable_diffusion_burn_b200 import parallel
     ctx = _lib.Context(local)
-    # ---- weights: rank 0 fills the fp32 master arena, ONE NCCL broadcast ships it (no per-step collective)
+    # ---- weights: rank 0 fills the fp32 master arena; ONE NCCL broadcast, issued by the library itself
+    # (sdb_broadcast_weights, include/sdb200.h), ships it over NVLink. No collective on the sampling path.
     if rank == 0:
         ctx.init_synthetic(0)
     bcast_ms = None
     if world > 1:
-        ptr, nbytes = ctx.weight_arena()
-
-        class _Arena:
-            __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-        arena = torch.as_tensor(_Arena(), device=f"cuda:{local}")
         torch.cuda.synchronize()
         dist.barrier()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        dist.broadcast(arena, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
+        t0 = time.perf_counter()
+        parallel.broadcast_weights(ctx, rank, world)
+        bcast_ms = (time.perf_counter() - t0) * 1e3  # includes ncclCommInitRank
     ctx.finalize_weights()
     if args.precision:
         ctx.set_option("precision", args.precision)
 
-    n, Hl = args.batch, args.size // 8
+    Hl = args.size // 8
     L, Lu = args.context_len, 2
-    # image index = rank*batch + i : every rank samples different images
-    h_ctx = synth.make_context(n, L, seed=77 + rank)
-    h_unc = synth.make_context(1, Lu, seed=99)[0]
-    h_lat = synth.make_latent(n, Hl, Hl, seed=1234 + rank * n)
     dev = torch.device("cuda", local)
-    d_ctx, d_unc, d_lat = (torch.from_numpy(a).to(dev) for a in (h_ctx, h_unc, h_lat))
-    d_rgb = torch.empty((n, 8 * Hl, 8 * Hl, 3), dtype=torch.uint8, device=dev)
-    p_ctx, p_unc, p_lat = (torch.from_numpy(a).pin_memory() for a in (h_ctx, h_unc, h_lat))
-    p_rgb = torch.empty((n, 8 * Hl, 8 * Hl, 3), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.current_stream()
 
-    def step_dev():
-        ctx.check(ctx.lib.sdb_sample_image_dev(ctx.h, d_ctx.data_ptr(), n, L, d_unc.data_ptr(), Lu, 7.5, args.ddim_steps,
-                                               d_lat.data_ptr(), Hl, Hl, d_rgb.data_ptr(), stream.cuda_stream))
+    def make_steps(n):
+        """(device-resident step, host-buffer end-to-end step, h2d bytes, d2h bytes) for a batch of n images per rank;
+        image index = rank*n + i: every rank samples different images."""
+        h_ctx = synth.make_context(n, L, seed=77 + rank)
+        h_unc = synth.make_context(1, Lu, seed=99)[0]
+        h_lat = synth.make_latent(n, Hl, Hl, seed=1234 + rank * n)
+        d_ctx, d_unc, d_lat = (torch.from_numpy(a).to(dev) for a in (h_ctx, h_unc, h_lat))
+        d_rgb = torch.empty((n, 8 * Hl, 8 * Hl, 3), dtype=torch.uint8, device=dev)
+        p_ctx, p_unc, p_lat = (torch.from_numpy(a).pin_memory() for a in (h_ctx, h_unc, h_lat))
+        p_rgb = torch.empty((n, 8 * Hl, 8 * Hl, 3), dtype=torch.uint8).pin_memory()
+        keep = (d_ctx, d_unc, d_lat, d_rgb, p_ctx, p_unc, p_lat, p_rgb)
 
-    def step_e2e():
-        # the public host-buffer call: H2D of context/uncond/latent, sampling, D2H of the u8 images — all inside
-        ctx.check(ctx.lib.sdb_sample_image(ctx.h, _lib.ptr(p_ctx.numpy()), n, L, _lib.ptr(p_unc.numpy()), Lu, 7.5, args.ddim_steps,
-                                           _lib.ptr(p_lat.numpy()), 0, Hl, Hl, p_rgb.numpy().ctypes.data_as(_lib._u8p)))
+        def dev_step(_k=keep):
+            ctx.check(ctx.lib.sdb_sample_image_dev(ctx.h, d_ctx.data_ptr(), n, L, d_unc.data_ptr(), Lu, 7.5, args.ddim_steps,
+                                                   d_lat.data_ptr(), Hl, Hl, d_rgb.data_ptr(), stream.cuda_stream))
+
+        def e2e_step(_k=keep):
+            # the public host-buffer call: H2D of context/uncond/latent, sampling, D2H of the u8 images — all inside
+            ctx.check(ctx.lib.sdb_sample_image(ctx.h, _lib.ptr(p_ctx.numpy()), n, L, _lib.ptr(p_unc.numpy()), Lu, 7.5, args.ddim_steps,
+                                               _lib.ptr(p_lat.numpy()), 0, Hl, Hl, p_rgb.numpy().ctypes.data_as(_lib._u8p)))
+        return dev_step, e2e_step, int(h_ctx.nbytes + h_unc.nbytes + h_lat.nbytes), int(p_rgb.numel())
+
+    n = args.batch
+    step_dev, step_e2e, h2d, d2h = make_steps(n)
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,8 +330,27 @@ def main():
     # the host-buffer call is synchronous: wall clock covers the copies too; take the larger of the two clocks
     ms_e2e = max(ms_e2e, wall * 1e3) if not dist else ms_e2e
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
-    h2d = int(h_ctx.nbytes + h_unc.nbytes + h_lat.nbytes)
-    d2h = int(p_rgb.numel())
+
+    # ---- BASELINE configs[4] (64 images sharded 8 per rank over 8 GPUs) as a sub-record whenever the job is multi-GPU:
+    # the same call with 8 images per rank (world * 8 images per step), its own clocks sample; the headline stays configs[1]
+    c5 = None
+    if world > 1 and args.batch != 8 and not args.no_c5:
+        c5_dev, c5_e2e, c5_h2d, c5_d2h = make_steps(8)
+        for _ in range(2):
+            c5_dev()
+        k5 = max(2, min(args.steps, 5))
+        s5 = ClockSampler(local)
+        if rank == 0:
+            s5.start()
+        ms5 = timed(c5_dev, k5)
+        clk5 = s5.stop() if rank == 0 else None
+        c5_e2e()
+        ms5e = timed(c5_e2e, k5)
+        c5 = {"workload": f"BASELINE configs[4]: SDv1-4 txt2img {args.size}x{args.size}, {args.ddim_steps} steps, cfg=7.5, "
+                          f"{8 * world} images sharded 8 per rank over {world} GPUs",
+              "value": world * 8 * k5 / (ms5 * 1e-3), "unit": UNIT, "steps": k5, "warmup": 2, "ms_per_step": ms5 / k5,
+              "images_per_step": 8 * world, "clocks": clk5,
+              "e2e": {"value": world * 8 * k5 / (ms5e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": c5_h2d, "d2h_bytes_per_step": c5_d2h}}
 
     # ---- per-kernel-class device time (graphs bypassed, every launch bracketed by events) for the roofline
     roof, classes = None, None
@@ -348,14 +367,17 @@ def main():
         ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/linear layers of one sample_image)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "peak_source": pk["src"] + " bf16 cuBLAS sustained (same tensor rate as fp16)",
-                "traffic": gemm_traffic_per_launch(), "launches": g["launches"], "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]),
-                "algorithmic_tflop_per_step": g["flops"] / 1e12, "issued_tflop_per_step": g["bytes"] / 1e12,
-                "share_of_step": g["ms"] / tot_ms if tot_ms else None,
+                "traffic": gemm_traffic_per_launch(), "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"]),
+                "launches": g["launches"], "avg_launch_us": g["ms"] * 1e3 / max(1, g["launches"]),
+                "algorithmic_tflop_per_step": g["flops"] / 1e12, "issued_tflop_per_step": g["issued_flops"] / 1e12,
+                # share of the REPLAYED step (the timed value), from event-bracketed launches: an upper bound, each bracket
+                # carries ~3 us of event overhead that graph replay does not pay
+                "share_of_step": g["ms"] / (ms / args.steps), "profile_mode_total_ms": tot_ms,
                 "whole_image_tflops": value / world * FLOP_PER_IMAGE / 1e12 if args.size == 512 and args.ddim_steps == 20 else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step_s, dec, threads, what = cpu_port_times(1, budget_s=30.0)
+        step_s, dec, threads, what = cpu_port_times(1, latent=Hl, ddim_steps_total=args.ddim_steps)
         cpu_img_s = args.ddim_steps * step_s[0] + dec
         cpu = {"value": 1.0 / cpu_img_s, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{what}; {step_s[0]:.2f} s/step x {args.ddim_steps} + decode {dec:.2f} s = {cpu_img_s:.1f} s/image"}
@@ -366,9 +388,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 tensor-core operands (3-term split-fp16 on the two high-res UNet levels), fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": f"SDv1-4 txt2img {args.size}x{args.size}, {args.ddim_steps} steps, cfg=7.5, batch={n} per GPU",
-                       "context_len": L, "precision_option": args.precision,
-                       "l2": "inputs larger than L2: >1.9 GB of packed weights stream from HBM every UNet step (L2 = 126 MB)"},
+            "config": workload_config(args, n),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -378,6 +398,8 @@ def main():
             "kernel_classes": classes,
             "weights_broadcast_ms": bcast_ms,
         }
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()

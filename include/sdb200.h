@@ -144,6 +144,8 @@ int sdb_profile_class_count(sdb_ctx* ctx);
 /* launches, total device milliseconds, algorithmic FLOPs and bytes of one kernel class. */
 int sdb_profile_get(sdb_ctx* ctx, int cls, const char** name, int64_t* launches, double* ms,
                     double* flops, double* bytes);
+/* tensor-core FLOPs actually issued by a class (x2 / x3 of the algorithmic count where the split-fp16 product runs). */
+int sdb_profile_get_issued(sdb_ctx* ctx, int cls, double* issued_flops);
 /* Number of kernel launches issued by this context since creation (sdb_profile_reset zeroes it). */
 int64_t sdb_launch_count(sdb_ctx* ctx);
 

@@ -63,6 +63,7 @@ SIGNATURES = [
     ("sdb_profile_class_count", C.c_int, [_ctx]),
     ("sdb_profile_get", C.c_int, [_ctx, C.c_int, C.POINTER(C.c_char_p), _i64p, C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sdb_profile_get_issued", C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double)]),
     ("sdb_launch_count", C.c_int64, [_ctx]),
     ("sdb_test_linear", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     ("sdb_test_conv2d", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -264,7 +265,9 @@ class Context:
         for i in range(self.lib.sdb_profile_class_count(self.h)):
             name = C.c_char_p(); ln = C.c_int64(); ms = C.c_double(); fl = C.c_double(); by = C.c_double()
             self.check(self.lib.sdb_profile_get(self.h, i, C.byref(name), C.byref(ln), C.byref(ms), C.byref(fl), C.byref(by)))
-            rows[name.value.decode()] = dict(launches=ln.value, ms=ms.value, flops=fl.value, bytes=by.value)
+            iss = C.c_double()
+            self.check(self.lib.sdb_profile_get_issued(self.h, i, C.byref(iss)))
+            rows[name.value.decode()] = dict(launches=ln.value, ms=ms.value, flops=fl.value, bytes=by.value, issued_flops=iss.value)
         return rows
 
     def launch_count(self):

@@ -434,7 +434,7 @@ int sdb_profile_reset(sdb_ctx* ctx) {
   API_BEGIN(ctx)
   profile_collect(c);
   c.launches = 0;
-  for (int i = 0; i < KC_COUNT; ++i) c.cls_ms[i] = c.cls_flops[i] = c.cls_bytes[i] = 0, c.cls_launches[i] = 0;
+  for (int i = 0; i < KC_COUNT; ++i) c.cls_ms[i] = c.cls_flops[i] = c.cls_bytes[i] = c.cls_issued[i] = 0, c.cls_launches[i] = 0;
   API_END
 }
 int sdb_profile_class_count(sdb_ctx*) { return KC_COUNT; }
@@ -447,6 +447,12 @@ int sdb_profile_get(sdb_ctx* ctx, int cls, const char** name, int64_t* launches,
   if (ms) *ms = c.cls_ms[cls];
   if (flops) *flops = c.cls_flops[cls];
   if (bytes) *bytes = c.cls_bytes[cls];
+  API_END
+}
+int sdb_profile_get_issued(sdb_ctx* ctx, int cls, double* issued_flops) {
+  API_BEGIN(ctx)
+  SDB_CHECK(cls >= 0 && cls < KC_COUNT && issued_flops, "class index");
+  *issued_flops = c.cls_issued[cls];
   API_END
 }
 int64_t sdb_launch_count(sdb_ctx* ctx) { return ctx ? ctx->c.launches : -1; }

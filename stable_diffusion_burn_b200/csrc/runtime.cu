@@ -71,11 +71,12 @@ const char* kernel_class_name(int cls) {
 }
 
 // ------------------------------------------------------------------ profiling scope
-KernelScope::KernelScope(Ctx& c_, int cls_, double flops, double bytes) : c(c_), cls(cls_), on(c_.profiling) {
+KernelScope::KernelScope(Ctx& c_, int cls_, double flops, double bytes, double issued) : c(c_), cls(cls_), on(c_.profiling) {
   c.launches++;
   c.cls_launches[cls]++;
   c.cls_flops[cls] += flops;
   c.cls_bytes[cls] += bytes;
+  c.cls_issued[cls] += issued;
   if (on) {
     ev.cls = cls;
     ev.flops = flops;
@@ -384,7 +385,13 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
 
   const double Mtot = (double)a0.n * a0.H * a0.W;
   const double flops = 2.0 * Mtot * (double)w.N * ((double)w.K + 64.0 * p.xkc);  // algorithmic (one product per MAC)
-  const double bytes = Mtot * Ctot * 2.0 + (double)w.N * w.K * 2.0 + Mtot * nout * 4.0;
+  // algorithmic bytes of one launch: every operand element read once in the formats the passes need, the
+  // result written once in every format it is produced in
+  const double a_bytes = Mtot * (Ctot + 64.0 * p.xkc) * 2.0 * (passes >= 2 ? 2 : 1);
+  const double w_bytes = (double)w.N * (w.K + 64.0 * p.xkc) * 2.0 * (passes >= 3 ? 2 : 1);
+  const double o_bytes = Mtot * nout * ((ep.out_f32 ? 4.0 : 0.0) + (ep.out_f16.hi ? 2.0 : 0.0) + (ep.out_f16.lo ? 2.0 : 0.0)) +
+                         (ep.residual ? Mtot * nout * 4.0 : 0.0);
+  const double bytes = a_bytes + w_bytes + o_bytes;  // per launch (a folded-upsample phase reads all of A and writes a quarter of the output)
 
   for (int phase = 0; phase < phases_out; ++phase) {
     const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
@@ -418,9 +425,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       p.tickets = c.splitk_tickets;
     }
     {
-      // flops = algorithmic 2*M*N*K of this launch; the class' second counter holds the ISSUED tensor-core
-      // FLOPs (x passes for split-fp16 products), not bytes
-      (void)bytes;
+      // flops = algorithmic 2*M*N*K of this launch; issued = the tensor-core FLOPs the passes really execute
       static const bool dbg_on = getenv("SDB_GEMM_DBG") != nullptr;
       static long long* dbg_buf = nullptr;
       if (dbg_on) {
@@ -431,7 +436,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       }
       const std::string label = c.dbg_label;
       {
-        KernelScope ks(c, KC_GEMM, flops, flops * passes);
+        KernelScope ks(c, KC_GEMM, flops, bytes, flops * passes);
         gemm_tc_launch(maps, p, BN, passes, c.stream);
       }
       if (dbg_on) {  // bring-up aid: cycle stamps of CTA (0,0,0), printed relative to kernel entry

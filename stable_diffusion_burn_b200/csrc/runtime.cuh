@@ -117,6 +117,7 @@ struct Ctx {
   std::vector<ProfEvent> prof;
   int64_t launches = 0;
   double cls_ms[KC_COUNT] = {0}, cls_flops[KC_COUNT] = {0}, cls_bytes[KC_COUNT] = {0};
+  double cls_issued[KC_COUNT] = {0};  // tensor-core FLOPs actually issued (x passes for split-fp16 products)
   int64_t cls_launches[KC_COUNT] = {0};
   // grow-only device staging for the host-buffer entry points (no cudaMalloc/cudaFree per call: each is a device-wide sync)
   struct IoBuf {
@@ -141,7 +142,7 @@ struct KernelScope {  // RAII: counts a launch, optionally brackets it with even
   int cls;
   bool on;
   ProfEvent ev;
-  KernelScope(Ctx& c, int cls, double flops = 0, double bytes = 0);
+  KernelScope(Ctx& c, int cls, double flops = 0, double bytes = 0, double issued = 0);
   ~KernelScope();
 };
 void profile_collect(Ctx& c);

@@ -31,14 +31,27 @@ def broadcast_arena(arena, src: int = 0):
     return arena
 
 
-def gather_images(local_images: np.ndarray, n_images: int, rank: int, world: int):
-    """local_images [k,H,W,3] uint8 for shard_images(...) -> [n_images,H,W,3] on rank 0 (None elsewhere)."""
+def broadcast_weights(ctx, rank: int, world: int):
+    """The ONE collective of the path, issued by the library (sdb_broadcast_weights): rank 0 creates an ncclUniqueId, the 128
+    bytes travel over the process group that already exists (any backend), every rank then joins the library's own communicator,
+    which broadcasts the fp32 master arena + the per-norm eps table from rank 0 and is destroyed."""
     import torch
     import torch.distributed as dist
+    box = [ctx.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, device=torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None)
+    ctx.broadcast_weights(box[0], rank, world)
+
+
+def gather_images(local_images: np.ndarray, n_images: int, rank: int, world: int):
+    """local_images [k,H,W,3] uint8 for shard_images(...) -> [n_images,H,W,3] on rank 0 (None elsewhere).
+    NCCL moves device memory only: under that backend the staging buffers live on the rank's current CUDA device."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     k_max = (n_images + world - 1) // world
     h, w, c = local_images.shape[1:]
-    pad = torch.zeros((k_max, h, w, c), dtype=torch.uint8)
-    pad[: local_images.shape[0]] = torch.from_numpy(local_images)
+    pad = torch.zeros((k_max, h, w, c), dtype=torch.uint8, device=dev)
+    pad[: local_images.shape[0]] = torch.from_numpy(local_images).to(dev)
     bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
     dist.gather(pad, bufs, dst=0)
     if rank != 0:
@@ -46,5 +59,5 @@ def gather_images(local_images: np.ndarray, n_images: int, rank: int, world: int
     out = np.zeros((n_images, h, w, c), np.uint8)
     for r in range(world):
         idx = shard_images(n_images, r, world)
-        out[idx] = bufs[r][: len(idx)].numpy()
+        out[idx] = bufs[r][: len(idx)].cpu().numpy()
     return out
