@@ -163,6 +163,12 @@ int sdb_test_gemm_ex(sdb_ctx* ctx, const float* a, const float* w, const float* 
 /* conv2d NCHW fp32 in/out through the implicit-GEMM path (3x3 pad 1 stride 1|2, or 1x1). */
 int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* bias, int n, int cin, int H,
                     int W, int cout, int ksize, int stride, int upsample, int passes, float* y);
+/* conv (3x3 pad 1 or 1x1) whose epilogue also leaves the GroupNorm statistics of its output, followed by the apply-only
+ * GroupNorm(+SiLU) that consumes them (the ResBlock's conv_in -> norm_out -> SiLU chain, unet/mod.rs:716-725). NCHW fp32 in/out;
+ * *slots = partial-statistics slots per image the GEMM wrote (> 0). */
+int sdb_test_conv_groupnorm(sdb_ctx* ctx, const float* x, const float* w, const float* bias, const float* gamma,
+                            const float* beta, int n, int cin, int H, int W, int cout, int ksize, int passes, int silu,
+                            float* y, int* slots);
 /* GroupNorm(32 groups)+optional SiLU, NCHW fp32 in/out. */
 int sdb_test_groupnorm(sdb_ctx* ctx, const float* x, const float* gamma, const float* beta, int n, int c,
                        int H, int W, int silu, float* y);

@@ -54,7 +54,32 @@ def set_emulation_policy(policy):
     _EMU["policy"] = policy
 
 
-def _q(x, role="a"):
+def set_emulation_fn(fn):
+    """Finest-grained study hook: fn(block tap name, parameter name, role) -> None (operand exact) | 'fp16' | 'bf16' | 'tf32'
+    | 'fp16+e4m3' (fp16 value plus an 8-bit-float correction of the rounding residual). Overrides the role/policy tables."""
+    _EMU["fn"] = fn
+
+
+def _round(x, m):
+    if m == "fp16":
+        return x.to(torch.float16).to(x.dtype)
+    if m == "bf16":
+        return x.to(torch.bfloat16).to(x.dtype)
+    if m == "tf32":
+        xi = x.to(torch.float32).view(torch.int32)
+        xi = (xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF
+        return xi.view(torch.float32).to(x.dtype)
+    if m == "fp16+e4m3":
+        hi = x.to(torch.float16).to(x.dtype)
+        lo = (x - hi) * 4096.0  # residual <= 2^-11 |x|: scaled into e4m3's normal range
+        return hi + lo.to(torch.float8_e4m3fn).to(x.dtype) / 4096.0
+    raise ValueError(m)
+
+
+def _q(x, role="a", name=None):
+    if _EMU.get("fn") is not None:
+        m = _EMU["fn"](_EMU["cur"], name, role)
+        return x if m is None else _round(x, m)
     m = _EMU["mode"]
     pol = _EMU.get("policy")
     roles = _EMU["roles"]
@@ -95,8 +120,8 @@ class Params:
 # ------------------------------------------------------------------ primitives
 def linear(P, name, x):
     """burn nn::Linear: y = x W + b, W stored [in,out] (reference src/model/load.rs:65-76)."""
-    xa = x if id(x) in _EMU.get("pre_rounded", ()) else _q(x, "a")  # see nn_layer_norm: LN-fused emulation
-    y = xa @ _q(P(f"{name}/weight"), "w")
+    xa = x if id(x) in _EMU.get("pre_rounded", ()) else _q(x, "a", name)  # see nn_layer_norm: LN-fused emulation
+    y = xa @ _q(P(f"{name}/weight"), "w", name)
     if P.has(f"{name}/bias"):
         y = y + P(f"{name}/bias")
     return y
@@ -105,7 +130,7 @@ def linear(P, name, x):
 def conv2d(P, name, x, stride=1, padding=0):
     """burn nn::conv::Conv2d -> at::conv2d, OIHW (reference src/model/load.rs:118-160)."""
     b = P(f"{name}/bias") if P.has(f"{name}/bias") else None
-    return F.conv2d(_q(x, "A"), _q(P(f"{name}/weight"), "W"), b, stride=stride, padding=padding)
+    return F.conv2d(_q(x, "A", name), _q(P(f"{name}/weight"), "W", name), b, stride=stride, padding=padding)
 
 
 def silu(x):

@@ -68,6 +68,8 @@ SIGNATURES = [
     ("sdb_test_linear", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     ("sdb_test_conv2d", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, _f32p]),
+    ("sdb_test_conv_groupnorm", C.c_int, [_ctx, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]),
     ("sdb_test_groupnorm", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     ("sdb_test_layernorm", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p]),
     ("sdb_test_attention", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
@@ -307,6 +309,16 @@ class Context:
         self.check(self.lib.sdb_test_conv2d(self.h, ptr(x), ptr(w), ptr(b) if b is not None else None, n, cin, H, W, cout,
                                             k, stride, upsample, passes, ptr(y)))
         return y
+
+    def test_conv_groupnorm(self, x, w, bias, gamma, beta, passes=3, silu=False):
+        x = f32(x); w = f32(w); bias = f32(bias); gamma = f32(gamma); beta = f32(beta)
+        n, cin, H, W = x.shape
+        cout, _, k, _ = w.shape
+        y = np.empty((n, cout, H, W), np.float32)
+        slots = C.c_int()
+        self.check(self.lib.sdb_test_conv_groupnorm(self.h, ptr(x), ptr(w), ptr(bias), ptr(gamma), ptr(beta), n, cin, H, W, cout, k,
+                                                    passes, 1 if silu else 0, ptr(y), C.byref(slots)))
+        return y, slots.value
 
     def test_groupnorm(self, x, gamma, beta, silu=False):
         x = f32(x); n, c, H, W = x.shape

@@ -414,6 +414,12 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_splitk_min_iters = value;
   else if (k == "splitk_chunk")
     c.opt_splitk_chunk = value < 1 ? 1 : value;
+  else if (k == "prefetch_w")
+    c.opt_prefetch_w = value;
+  else if (k == "mlp_passes")
+    c.opt_mlp_passes = value;
+  else if (k == "gn_epilogue")
+    c.opt_gn_epilogue = value;
   else if (k == "skip_merge")
     c.opt_skip_merge = value;
   else if (k == "gn_min_pix")
@@ -609,6 +615,61 @@ int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* b
   ep.bias = d_b;
   run_gemm(c, kind, A, nullptr, Wp, passes, ep);
   nhwc_to_nchw_launch(d_yh, n, cout, Ho, Wo, d_y, c.stream);
+  SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * yout, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int sdb_test_conv_groupnorm(sdb_ctx* ctx, const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                            int n, int cin, int H, int W, int cout, int ksize, int passes, int silu, float* y, int* used_epilogue_stats) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  SDB_CHECK(ksize == 1 || ksize == 3, "ksize");
+  const size_t xin = (size_t)n * cin * H * W, yout = (size_t)n * cout * H * W;
+  auto up = [&](const float* h, size_t cnt) {
+    float* d = c.work.get<float>(cnt);
+    SDB_CUDA(cudaMemcpyAsync(d, h, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
+    return d;
+  };
+  float* d_x = up(x, xin);
+  float* d_w = up(w, (size_t)cout * cin * ksize * ksize);
+  float* d_b = bias ? up(bias, cout) : nullptr;
+  float* d_g = up(gamma, cout);
+  float* d_be = up(beta, cout);
+  float* d_xh = c.work.get<float>(xin);
+  float* d_conv = c.work.get<float>(yout);
+  float* d_yh = c.work.get<float>(yout);
+  float* d_y = c.work.get<float>(yout);
+  nchw_to_nhwc_launch(d_x, n, cin, H, W, d_xh, c.stream);
+  ActOp A;
+  A.n = n, A.C = cin, A.H = H, A.W = W;
+  A.p = Half2Ptr{c.work.get<__half>(xin), c.work.get<__half>(xin)};
+  prep_operand_launch(d_xh, cin, nullptr, 0, n, H, W, 0, nullptr, nullptr, nullptr, 0.f, A.p, c.stream);
+  WeightOp Wp;
+  Wp.N = cout, Wp.K = ksize * ksize * cin;
+  Wp.p = Half2Ptr{c.work.get<__half>((size_t)cout * Wp.K), c.work.get<__half>((size_t)cout * Wp.K)};
+  pack_conv_launch(d_w, cout, cin, ksize, Wp.p, c.stream);
+  GnPart gn;
+  gn.bucket = cout % 320 == 0 ? 10 : cout / 32;
+  gn.cap = std::max(3 * ((H * W + 127) / 128), 160);
+  gn.buf = c.work.get<float>((size_t)n * gn.cap * (cout / gn.bucket) * 2);
+  Epilogue ep;
+  ep.out_f32 = d_conv, ep.bias = d_b, ep.gn = &gn;
+  run_gemm(c, ksize == 1 ? G_CONV1 : G_CONV3, A, nullptr, Wp, passes, ep);
+  if (used_epilogue_stats) *used_epilogue_stats = gn.slots;
+  SDB_CHECK(gn.slots > 0, "the GEMM did not produce GroupNorm statistics for this shape");
+  Half2Ptr o16{c.work.get<__half>(yout), c.work.get<__half>(yout)};
+  GnSrc s0, s1;
+  s0.x = d_conv, s0.C = cout, s0.part = gn.buf, s0.cap = gn.cap, s0.slots = gn.slots;
+  gn_apply_launch(s0, s1, gn.bucket, n, H, W, silu, d_g, d_be, 1e-5f, o16, c.stream);
+  std::vector<__half> hi(yout), lo(yout);
+  SDB_CUDA(cudaMemcpyAsync(hi.data(), o16.hi, yout * 2, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(lo.data(), o16.lo, yout * 2, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<float> nhwc(yout);
+  for (size_t i = 0; i < yout; ++i) nhwc[i] = __half2float(hi[i]) + __half2float(lo[i]);
+  SDB_CUDA(cudaMemcpyAsync(d_yh, nhwc.data(), yout * 4, cudaMemcpyHostToDevice, c.stream));
+  nhwc_to_nchw_launch(d_yh, n, cout, H, W, d_y, c.stream);
   SDB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(float) * yout, cudaMemcpyDeviceToHost, c.stream));
   SDB_CUDA(cudaStreamSynchronize(c.stream));
   API_END

@@ -153,6 +153,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): warms L2 for a later load of the same box
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+
 // 2-SM (cta_group::2) loads: data lands in the issuing CTA's smem, the transaction bytes are reported to an
 // mbarrier that may live in the peer CTA of the pair (shared::cluster address, see mapa_shared)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {

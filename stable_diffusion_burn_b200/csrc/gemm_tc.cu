@@ -52,6 +52,50 @@ __device__ __noinline__ void epilogue_store(float4 f, unsigned int o32, unsigned
   }
 }
 
+// Bucket reduction of the per-quarter column sums an epilogue left in shared memory (cs[q][col] = (sum, sumsq) of the 32 rows of
+// lane quarter q), written as this tile's GroupNorm partials. `nq` quarters per image slice (4 = the whole tile is one image).
+// which images the 128 rows of this tile belong to: g_tn images per tile (1, 2 or 4), the first one, the tile's index inside it
+struct GnTile {
+  int tn, img0, tile, nimg;
+};
+__device__ __forceinline__ GnTile gn_tile_of(const GemmParams& p, int n0, int th, int tw) {
+  GnTile g;
+  if (p.gn_rpi) {  // flattened rows: blockIdx.x is the row tile
+    g.nimg = p.gn_nimg;
+    if (p.gn_rpi >= BM)
+      g.tn = 1, g.img0 = (tw * BM) / p.gn_rpi, g.tile = ((tw * BM) % p.gn_rpi) / BM;
+    else
+      g.tn = BM / p.gn_rpi, g.img0 = tw * g.tn, g.tile = 0;
+  } else {
+    g.tn = p.TN, g.img0 = n0, g.tile = th * p.tiles_w + tw, g.nimg = p.nimg;
+  }
+  return g;
+}
+__device__ __forceinline__ void gn_write_partials(const GemmParams& p, const float2* cs, int BN, int te, int nthreads, const GnTile g,
+                                                  int col0, int z) {
+  const int nbk_tile = BN / p.gn_bucket, nbk_total = p.N / p.gn_bucket;
+  const int qpi = 4 / g.tn;  // lane quarters per image (1, 2 or 4 images per tile: checked by run_gemm)
+  const int slot = p.gn_slot0 + g.tile * p.split_k + z;
+  // thread = (bucket, quarter): 4 adjacent lanes hold the quarters of one bucket and combine them with shuffles in a fixed
+  // order (nbk_tile * 4 <= 256 threads: BN <= 256, bucket >= 4); whole warps take part so that the shuffles are convergent
+  (void)nthreads;
+  if (te < ((nbk_tile * 4 + 31) & ~31)) {
+    const int b = te >> 2, q = te & 3;
+    float sm = 0.f, sq = 0.f;
+    if (b < nbk_tile) {
+      const float2* src = cs + q * BN + b * p.gn_bucket;
+      for (int c = 0; c < p.gn_bucket; ++c) sm += src[c].x, sq += src[c].y;
+    }
+    if (qpi >= 2) sm += __shfl_xor_sync(0xffffffffu, sm, 1), sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    if (qpi == 4) sm += __shfl_xor_sync(0xffffffffu, sm, 2), sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    const int k = q / qpi, img = g.img0 + k, c0 = b * p.gn_bucket;
+    if (b < nbk_tile && (q % qpi) == 0 && img < g.nimg && col0 + c0 < p.N) {
+      float2* dst = reinterpret_cast<float2*>(p.gn_part) + ((size_t)img * p.gn_cap + slot) * nbk_total + (col0 + c0) / p.gn_bucket;
+      *dst = make_float2(sm, sq);
+    }
+  }
+}
+
 // Variants whose pipeline fits twice in an SM's shared memory are launched two CTAs per SM (<= 102 registers per thread);
 // the others own the SM and may use the whole register file.
 template <int BN, int PASSES, int STAGES, int CG>
@@ -66,9 +110,15 @@ __host__ __device__ constexpr int epilogue_warps() {
   return 8;
 }
 
-template <int BN, int PASSES, int STAGES, int CG>
+// EPI selects what the epilogue does beside bias / residual / stores. It is a compile-time choice because the once-per-CTA
+// epilogue is instruction-issue bound: statistics code that is merely skipped at run time still cost ~0.5 us per launch.
+//   EPI_PLAIN  nothing more          EPI_GN   GroupNorm statistics of the output tensor (column sums per channel bucket)
+enum : int { EPI_PLAIN = 0, EPI_GN = 1 };
+
+template <int BN, int PASSES, int STAGES, int CG, int EPI>
 __global__ void __launch_bounds__(64 + 32 * epilogue_warps<BN, PASSES, STAGES, CG>(), min_ctas_per_sm<BN, PASSES, STAGES, CG>())
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  constexpr bool kGN = EPI == EPI_GN;
   using L = StageLayout<BN, PASSES, CG>;
   constexpr bool TWO = CG == 2;
   constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();  // epilogue warps
@@ -136,49 +186,80 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
-
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail. From here on each role waits for the
+  // previous kernel (griddepcontrol.wait) only where it first touches data that kernel may have written:
+  //   producer : WEIGHTS are immutable, so the weight tiles of the first STAGES k-chunks (and an L2 prefetch of the rest of this
+  //              CTA's weight strip when the launch is weight-bound) are issued BEFORE the wait; activation tiles after it
+  //   MMA warp : consumes shared memory behind the mbarriers only: no wait
+  //   epilogue : waits before its first read of residual / time-embedding rows; all of this kernel's stores follow that wait
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (leader) mbar_expect_tx(&full_bar[s], L::BYTES * CG);  // both CTAs' loads report to the leader's barrier
-        uint8_t* st = smem + s * L::BYTES;
-        // iteration -> (activation source, channel chunk, tap shift) and the weight map / K coordinate that go with it
-        int src, c0, cw, ch, cp, bk;
-        const CUtensorMap* bm;
+      // iteration -> (activation source, channel chunk, tap shift) and the weight map / K coordinate that go with it
+      auto load_b = [&](int it, int s) {
+        const CUtensorMap* bm = it < main_iters ? maps.b : maps.bx;
+        const int bk = (it < main_iters ? it : it - main_iters) * BK;
+        uint8_t* sb = smem + s * L::BYTES + L::A_TILES * A_TILE_BYTES;
+        if (!TWO) {
+          tma_load_2d(sb, &bm[0], &full_bar[s], bk, col0);
+          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &bm[1], &full_bar[s], bk, col0);
+        } else {
+          // rows [crank*BN/2, +BN/2) of the weight tile into this CTA's smem, bytes reported to the leader's barrier
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+          tma_load_2d_2sm(sb, &bm[0], fb, bk, col0 + crank * (BN / 2));
+          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &bm[1], fb, bk, col0 + crank * (BN / 2));
+        }
+      };
+      auto load_a = [&](int it, int s) {
+        int src, c0, cw, ch, cp;
         if (it < main_iters) {
           const int tap = it / p.kc;
           const int cc = it - tap * p.kc;
           src = cc >= p.kc0 ? 1 : 0;
           c0 = (cc - (src ? p.kc0 : 0)) * BK;
           cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
-          bm = maps.b, bk = it * BK;
         } else {
           const int e = it - main_iters;
           src = e >= p.xkc0 ? 3 : 2;
           c0 = (e - (src == 3 ? p.xkc0 : 0)) * BK;
           cw = w0, ch = h0, cp = 0;
-          bm = maps.bx, bk = e * BK;
         }
-        uint8_t* sb = st + L::A_TILES * A_TILE_BYTES;
+        uint8_t* st = smem + s * L::BYTES;
         if (!TWO) {
           tma_load_5d(st, &maps.a[src][0], &full_bar[s], c0, cw, ch, cp, n0);
           if (PASSES >= 2) tma_load_5d(st + A_TILE_BYTES, &maps.a[src][1], &full_bar[s], c0, cw, ch, cp, n0);
-          tma_load_2d(sb, &bm[0], &full_bar[s], bk, col0);
-          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &bm[1], &full_bar[s], bk, col0);
         } else {
-          // own 128 A rows + rows [crank*BN/2, +BN/2) of the weight tile, into this CTA's smem
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
           tma_load_5d_2sm(st, &maps.a[src][0], fb, c0, cw, ch, cp, n0);
           if (PASSES >= 2) tma_load_5d_2sm(st + A_TILE_BYTES, &maps.a[src][1], fb, c0, cw, ch, cp, n0);
-          tma_load_2d_2sm(sb, &bm[0], fb, bk, col0 + crank * (BN / 2));
-          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &bm[1], fb, bk, col0 + crank * (BN / 2));
         }
-        if (dbg && it == it_begin) dbg[2] = clock64();
+      };
+      // ---- before the wait: weights only (the pipeline slots are all free: fresh barriers)
+      const int npre = min(STAGES, it_end - it_begin);
+      for (int i = 0; i < npre; ++i) {
+        if (leader) mbar_expect_tx(&full_bar[i], L::BYTES * CG);  // A + B bytes of both CTAs report to the leader's barrier
+        load_b(it_begin + i, i);
+      }
+      if (p.prefetch_w) {
+        for (int it = it_begin + npre; it < it_end; ++it) {
+          const CUtensorMap* bm = it < main_iters ? maps.b : maps.bx;
+          const int bk = (it < main_iters ? it : it - main_iters) * BK;
+          const int row = col0 + (TWO ? crank * (BN / 2) : 0);
+          tma_prefetch_l2_2d(&bm[0], bk, row);
+          if (PASSES >= 3) tma_prefetch_l2_2d(&bm[1], bk, row);
+        }
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i) load_a(it_begin + i, i);
+      if (dbg) dbg[2] = clock64();
+      // ---- steady state
+      int s = npre == STAGES ? 0 : npre;
+      uint32_t ph = npre == STAGES ? 1 : 0;
+      for (int it = it_begin + npre; it < it_end; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) mbar_expect_tx(&full_bar[s], L::BYTES * CG);
+        load_a(it, s);
+        load_b(it, s);
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
@@ -232,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
   } else {
     // ===================================================== epilogue (warps 2..9)
+    pdl_wait();  // residual / time-embedding rows below may come from the previous kernel; every store of this kernel follows
     // Each thread owns one accumulator row in TMEM (warp w may touch lanes 32*(w%4)..+31); the two warps that
     // share a lane quarter split the 32-column chunks between them. A row-per-thread store pattern would touch 32
     // cache lines per instruction, so every 32x32 block is transposed through shared memory (the pipeline stages
@@ -312,6 +394,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       return f;
     };
     // element offsets fit 32 bits (run_gemm checks rows * ld < 2^31): one IMAD per row instead of 64-bit address chains
+    // GroupNorm statistics of the output (p.gn_part): per-quarter column sums, staged in the second transposition bank
+    // (which only the GEGLU epilogue uses; run_gemm never combines the two)
+    float2* const gn_cs = reinterpret_cast<float2*>(smem + EW * 32 * TROW);
+    const GnTile gnt = gn_tile_of(p, n0, th, tw);
     auto store_out = [&](float4 f, int mr, int col) {
       epilogue_store(f, (unsigned)(mr * p.ldc + col), (unsigned)(mr * p.ldc16 + col), p.out_f32, p.out_f16, p.out_f16_lo, p.act);
     };
@@ -355,11 +441,19 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int rows_per = (BM + p.split_k - 1) / p.split_k;
         const int r0 = blockIdx.z * rows_per, r1 = min(BM, r0 + rows_per);
         constexpr int C4 = BN / 4;
+        // thread -> (row lane, fixed 4-column group): a thread's GroupNorm column sums stay in registers across its rows
+        constexpr int RL = (EW * 32) / C4;  // row lanes
         const int te = threadIdx.x - 64;
+        const int rlane = te / C4, cg4 = te - rlane * C4;
+        const int rpi = BM / gnt.tn;  // rows per image inside the tile
+        float4* const gn_red = reinterpret_cast<float4*>(smem + EW * 32 * TROW);  // [RL][TN][C4][2] float4, <= 32 KB (second bank)
 #pragma unroll 1
-        for (int idx = te; idx < (r1 - r0) * C4; idx += EW * 32) {
-          const int rl = r0 + idx / C4;
-          const int col = col0 + (idx % C4) * 4;
+        for (int k = 0; k < gnt.tn; ++k) {
+        float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f), gsq = gsum;
+        const int row_a = max(r0, k * rpi), row_b = min(r1, (k + 1) * rpi);
+#pragma unroll 1
+        for (int rl = row_a + rlane; rlane < RL && rl < row_b; rl += RL) {
+          const int col = col0 + cg4 * 4;
           const int qw = w0 + rl % p.TW, qh = h0 + (rl / p.TW) % p.TH, qn = n0 + rl / (p.TW * p.TH);
           if (qw < p.W && qh < p.H && qn < p.nimg && col < p.N) {
             const int mr = (qn * p.OH + qh * p.os + p.oa) * p.OW + qw * p.os + p.ob;
@@ -390,7 +484,36 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
             acc.x += bv.x + rb.x + rs.x, acc.y += bv.y + rb.y + rs.y;
             acc.z += bv.z + rb.z + rs.z, acc.w += bv.w + rb.w + rs.w;
+            if constexpr (kGN) {
+              gsum.x += acc.x, gsum.y += acc.y, gsum.z += acc.z, gsum.w += acc.w;
+              gsq.x = fmaf(acc.x, acc.x, gsq.x), gsq.y = fmaf(acc.y, acc.y, gsq.y), gsq.z = fmaf(acc.z, acc.z, gsq.z), gsq.w = fmaf(acc.w, acc.w, gsq.w);
+            }
             store_out(acc, mr, col);
+          }
+        }
+        if (kGN && rlane < RL) {
+          gn_red[((rlane * gnt.tn + k) * C4 + cg4) * 2] = gsum;
+          gn_red[((rlane * gnt.tn + k) * C4 + cg4) * 2 + 1] = gsq;
+        }
+        }
+        if constexpr (kGN) {
+          // fold the row lanes in a fixed order, then the channel buckets: this CTA's partial for its slice of the tile rows
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          const int nbk_tile = BN / p.gn_bucket, nbk_total = p.N / p.gn_bucket;
+          const int slot = p.gn_slot0 + gnt.tile * p.split_k + blockIdx.z;
+          const float* red = reinterpret_cast<const float*>(gn_red);
+          for (int it = te; it < gnt.tn * nbk_tile; it += EW * 32) {
+            const int k = it / nbk_tile, b = it - k * nbk_tile;
+            const int img = gnt.img0 + k, c0 = b * p.gn_bucket;
+            if (img >= gnt.nimg || col0 + c0 >= p.N) continue;
+            float sm = 0.f, sq = 0.f;
+            for (int l = 0; l < RL; ++l)
+              for (int cc = c0; cc < c0 + p.gn_bucket; ++cc) {
+                const int base = (((l * gnt.tn + k) * C4 + (cc >> 2)) * 2) * 4 + (cc & 3);
+                sm += red[base], sq += red[base + 4];
+              }
+            float2* dst = reinterpret_cast<float2*>(p.gn_part) + ((size_t)img * p.gn_cap + slot) * nbk_total + (col0 + c0) / p.gn_bucket;
+            *dst = make_float2(sm, sq);
           }
         }
       }
@@ -447,6 +570,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           stage(tile_s, v);
           __syncwarp();
           const int col = col0 + c + cq;
+          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f), gsq = gsum;
           if (col < p.N) {
             const uint32_t tl = tile_s + sub * TROW + cq * 4;
 #pragma unroll
@@ -464,15 +588,38 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 if (mr8[k] < 0) continue;
                 float4 f = t[i];
                 f.x += bvs[j].x + ad[k].x, f.y += bvs[j].y + ad[k].y, f.z += bvs[j].z + ad[k].z, f.w += bvs[j].w + ad[k].w;
+                if constexpr (kGN) {
+                  gsum.x += f.x, gsum.y += f.y, gsum.z += f.z, gsum.w += f.w;
+                  gsq.x = fmaf(f.x, f.x, gsq.x), gsq.y = fmaf(f.y, f.y, gsq.y), gsq.z = fmaf(f.z, f.z, gsq.z), gsq.w = fmaf(f.w, f.w, gsq.w);
+                }
                 epilogue_store(f, (unsigned)(mr8[k] * p.ldc + col), (unsigned)(mr8[k] * p.ldc16 + col), p.out_f32, p.out_f16,
                                p.out_f16_lo, p.act);
               }
+            }
+          }
+          if constexpr (kGN) {
+            // the 4 lanes that hold the same columns (sub = 0..3) fold in a fixed order; sub 0 publishes the quarter's 32-row sums
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              gsum.x += __shfl_xor_sync(0xffffffffu, gsum.x, o), gsum.y += __shfl_xor_sync(0xffffffffu, gsum.y, o);
+              gsum.z += __shfl_xor_sync(0xffffffffu, gsum.z, o), gsum.w += __shfl_xor_sync(0xffffffffu, gsum.w, o);
+              gsq.x += __shfl_xor_sync(0xffffffffu, gsq.x, o), gsq.y += __shfl_xor_sync(0xffffffffu, gsq.y, o);
+              gsq.z += __shfl_xor_sync(0xffffffffu, gsq.z, o), gsq.w += __shfl_xor_sync(0xffffffffu, gsq.w, o);
+            }
+            if (sub == 0) {
+              float2* d = gn_cs + q * BN + c + cq;
+              d[0] = make_float2(gsum.x, gsq.x), d[1] = make_float2(gsum.y, gsq.y);
+              d[2] = make_float2(gsum.z, gsq.z), d[3] = make_float2(gsum.w, gsq.w);
             }
           }
           __syncwarp();
           // the next chunk's addends travel while its accumulator columns are read and staged
           if (j + 1 < NCH && c + CSTEP < BN) issue_addends(col0 + c + CSTEP + cq);
         }
+      }
+      if constexpr (kGN) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");  // every quarter's column sums are in shared memory
+        gn_write_partials(p, gn_cs, BN, threadIdx.x - 64, EW * 32, gnt, col0, 0);
       }
     }
     tc_fence_before();
@@ -509,14 +656,16 @@ constexpr int pick_stages_half() {
   return n > 4 ? 4 : (n < 2 ? 2 : n);
 }
 
-template <int BN, int PASSES, int STAGES, int CG>
-static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int PASSES, int STAGES, int CG, int EPI>
+static void launch_epi(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem = STAGES * StageLayout<BN, PASSES, CG>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
   constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();
   static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 2 * EW * 32 * 144, "epilogue staging tiles must fit in the stages");
+  static_assert(4 * BN * 8 <= EW * 32 * 144 && ((EW * 32) / (BN / 4)) * 4 * (BN / 4) * 32 <= EW * 32 * 144,
+                "GroupNorm column sums must fit in the second staging bank");
   static DeviceOnce once;
   if (once.first())
-    SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = dim3(64 + 32 * EW), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
@@ -526,7 +675,17 @@ static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 2 : 1;
-  SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES, CG>, maps, p));
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, STAGES, CG, EPI>, maps, p));
+}
+
+// the statistics-producing epilogues exist for the tile widths their tensors use (run_gemm checks with gemm_tc_supports_epi)
+template <int BN, int PASSES, int STAGES, int CG>
+static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+  if constexpr (BN >= 128) {
+    if (p.gn_part) return launch_epi<BN, PASSES, STAGES, CG, EPI_GN>(maps, p, stream);
+  }
+  SDB_CHECK(!p.gn_part, "GroupNorm statistics are not built for this tile width");
+  launch_epi<BN, PASSES, STAGES, CG, EPI_PLAIN>(maps, p, stream);
 }
 
 template <int BN, int PASSES, int CG>

@@ -331,6 +331,156 @@ gn_fused_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
   }
 }
 
+// ============================================================ GroupNorm apply from producer-side statistics
+// The GEMM that wrote the tensor also left per-(image, slot, channel-bucket) partial sums (gemm_tc.cuh: gn_part). Every CTA folds
+// the partials of its image in a fixed order (fp64), derives the per-channel affine and makes ONE pass over its pixel chunk:
+// x read once, no statistics pass, no grid rendezvous. Reads the two sources of cat([x0, x1]) directly.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const GnSrc s0, const GnSrc s1, int bucket, int H, int W, int pix_per_cta, int silu,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ out_hi,
+                __half* __restrict__ out_lo) {
+  pdl_enter();
+  extern __shared__ float s_dyn[];  // scale[C], shift[C]
+  __shared__ double s_bsum[2 * 256];  // (sum, sumsq) per channel bucket of the concat, C / bucket <= 256
+  __shared__ double s_gsum[64];
+  const int n = blockIdx.y;
+  const int C0 = s0.C, C1 = s1.C, C = C0 + C1, gs = C / 32, HW = H * W;
+  const int nb0 = C0 / bucket, nbt = C / bucket;
+  // fold of the producer's partial slots. A serial walk would be a chain of L2 round trips (~0.35 us each): the slots of one
+  // (bucket, stat) item are spread over `lanes` threads, four loads in flight each, and the lanes are combined in index order
+  // (fixed order everywhere -> every CTA of the image derives bit-identical statistics)
+  __shared__ double s_lane[512];
+  {
+    const int items = 2 * nbt;
+    const int lanes = items >= 256 ? 1 : 256 / items;
+    for (int idx = threadIdx.x; idx < items * lanes; idx += blockDim.x) {
+      const int t = idx % items, lane = idx / items;
+      const int b = t >> 1, which = t & 1;
+      const GnSrc& s = b < nb0 ? s0 : s1;
+      const int nbk = s.C / bucket, bb = b < nb0 ? b : b - nb0;
+      const float* p = s.part + ((size_t)n * s.cap * nbk + bb) * 2 + which;
+      const size_t st = (size_t)nbk * 2;
+      double a = 0.0;
+      int sl = lane;
+      for (; sl + 3 * lanes < s.slots; sl += 4 * lanes) {
+        const float v0 = __ldcg(p + sl * st), v1 = __ldcg(p + (sl + lanes) * st);
+        const float v2 = __ldcg(p + (sl + 2 * lanes) * st), v3 = __ldcg(p + (sl + 3 * lanes) * st);
+        a += (double)v0, a += (double)v1, a += (double)v2, a += (double)v3;
+      }
+      for (; sl < s.slots; sl += lanes) a += (double)__ldcg(p + sl * st);
+      s_lane[lane * items + t] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < items; t += blockDim.x) {
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += s_lane[l * items + t];
+      s_bsum[t] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1, bpg = gs / bucket;
+    double a = 0.0;
+    for (int i = 0; i < bpg; ++i) a += s_bsum[(g * bpg + i) * 2 + which];
+    s_gsum[threadIdx.x] = a;
+  }
+  __syncthreads();
+  float* s_scale = s_dyn;
+  float* s_shift = s_dyn + C;
+  {
+    const double inv_cnt = 1.0 / ((double)gs * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / gs;
+      const double mean = s_gsum[g * 2] * inv_cnt;
+      double var = s_gsum[g * 2 + 1] * inv_cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float sc = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = beta[c] - (float)mean * sc;
+    }
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const int c8n = C / 8;
+  const int items = (p1 - p0) * c8n;
+  const float* x0 = s0.x;
+  const float* x1 = s1.x;
+  auto src_of = [&](int i, int& p, int& c) {
+    p = p0 + i / c8n;
+    c = (i - (i / c8n) * c8n) * 8;
+    return (c < C0) ? x0 + ((size_t)n * HW + p) * C0 + c : x1 + ((size_t)n * HW + p) * C1 + (c - C0);
+  };
+  auto finish = [&](float4 a, float4 b, int p, int c) {
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], s_scale[c + j], s_shift[c + j]);
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+    const size_t o = ((size_t)n * HW + p) * C + c;
+    split_store8(f, out_hi + o, out_lo ? out_lo + o : nullptr);
+  };
+  // two items per thread and iteration: 4 independent 16-byte loads in flight before the first use
+  int i = threadIdx.x;
+  for (; i + (int)blockDim.x < items; i += 2 * blockDim.x) {
+    int pa, ca, pb, cb;
+    const float* sa = src_of(i, pa, ca);
+    const float* sb = src_of(i + blockDim.x, pb, cb);
+    const float4 a0 = __ldcs(reinterpret_cast<const float4*>(sa)), a1 = __ldcs(reinterpret_cast<const float4*>(sa + 4));
+    const float4 b0 = __ldcs(reinterpret_cast<const float4*>(sb)), b1 = __ldcs(reinterpret_cast<const float4*>(sb + 4));
+    finish(a0, a1, pa, ca);
+    finish(b0, b1, pb, cb);
+  }
+  if (i < items) {
+    int pa, ca;
+    const float* sa = src_of(i, pa, ca);
+    finish(*reinterpret_cast<const float4*>(sa), *reinterpret_cast<const float4*>(sa + 4), pa, ca);
+  }
+}
+
+// Large images leave thousands of partial slots (one per 128-pixel tile): a first pass folds groups of 64 slots (fp64 inside,
+// fixed order) so that the apply kernel's per-CTA fold stays short. in [n][cap][nbk][2] -> out [n][ceil(slots/64)][nbk][2].
+__global__ void __launch_bounds__(256)
+gn_fold_kernel(const float* __restrict__ part, int cap, int slots, int nbk2, float* __restrict__ out) {
+  pdl_enter();
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int s0 = chunk * 64, s1 = min(slots, s0 + 64);
+  for (int t = threadIdx.x; t < nbk2; t += blockDim.x) {
+    const float* p = part + ((size_t)n * cap + s0) * nbk2 + t;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int sl = 0;
+    const int cnt = s1 - s0;
+    for (; sl + 3 < cnt; sl += 4) {
+      a0 += (double)__ldcg(p + (size_t)sl * nbk2), a1 += (double)__ldcg(p + (size_t)(sl + 1) * nbk2);
+      a2 += (double)__ldcg(p + (size_t)(sl + 2) * nbk2), a3 += (double)__ldcg(p + (size_t)(sl + 3) * nbk2);
+    }
+    for (; sl < cnt; ++sl) a0 += (double)__ldcg(p + (size_t)sl * nbk2);
+    out[((size_t)n * nchunks + chunk) * nbk2 + t] = (float)((a0 + a1) + (a2 + a3));
+  }
+}
+int gn_fold_slots(int slots) { return (slots + 63) / 64; }
+void gn_fold_launch(const float* part, int cap, int slots, int nbk, int n, float* out, cudaStream_t st) {
+  dim3 grid(gn_fold_slots(slots), n);
+  launch_k(gn_fold_kernel, grid, dim3(256), 0, st, part, cap, slots, nbk * 2, out);
+  SDB_CUDA(cudaGetLastError());
+}
+
+void gn_apply_launch(const GnSrc& s0, const GnSrc& s1, int bucket, int n, int H, int W, int silu, const float* gamma,
+                     const float* beta, float eps, Half2Ptr out, cudaStream_t st) {
+  const int C = s0.C + s1.C, HW = H * W;
+  SDB_CHECK(C % 64 == 0 && s0.C % 8 == 0 && C <= 2560 && bucket > 0 && s0.C % bucket == 0 && s1.C % bucket == 0 &&
+                (C / 32) % bucket == 0 && C / bucket <= 256,
+            "GroupNorm apply: channel / bucket geometry");
+  // no co-residency constraint any more: ~4 CTAs per SM, at least one pixel each
+  int pix = (int)((((long long)HW * n) + 591) / 592);
+  if (pix < 1) pix = 1;
+  dim3 grid(ceil_div(HW, pix), n);
+  launch_k(gn_apply_kernel, grid, dim3(256), (size_t)2 * C * sizeof(float), st, s0, s1, bucket, H, W, pix, silu, gamma, beta, eps,
+           out.hi, out.lo);
+  SDB_CUDA(cudaGetLastError());
+}
+
 int g_gn_min_pix = 1;  // pixels per CTA floor: small feature maps are latency-bound, so they get many small CTAs
 static int gn_fused_pix(int n, int HW) {
   int pix = (int)((((long long)HW * n) + 295) / 296);  // <= 296 CTAs (2 per SM): short fold, always co-resident

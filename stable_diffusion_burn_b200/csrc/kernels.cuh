@@ -23,6 +23,19 @@ extern int g_gn_min_pix;
 size_t gn_fused_partial_floats(int n, int HW);
 void gn_fused_launch(const float* x0, int C0, const float* x1, int C1, int n, int H, int W, int silu, const float* gamma,
                      const float* beta, float eps, Half2Ptr out, float* partials, unsigned int* tickets, cudaStream_t st);
+// GroupNorm(+SiLU) -> fp16 hi(/lo) operand from statistics the producing GEMM left beside the tensor (gemm_tc.cuh: gn_part):
+// one read of x, no statistics pass, no rendezvous. part = [n][cap][C / bucket][2] floats, `slots` of the cap written.
+struct GnSrc {
+  const float* x = nullptr;
+  int C = 0;
+  const float* part = nullptr;
+  int cap = 0, slots = 0;
+};
+// folds groups of 64 partial slots: out [n][gn_fold_slots(slots)][nbk][2]
+int gn_fold_slots(int slots);
+void gn_fold_launch(const float* part, int cap, int slots, int nbk, int n, float* out, cudaStream_t st);
+void gn_apply_launch(const GnSrc& s0, const GnSrc& s1, int bucket, int n, int H, int W, int silu, const float* gamma,
+                     const float* beta, float eps, Half2Ptr out, cudaStream_t st);
 // mode bits
 enum : int { PREP_NORM = 1, PREP_SILU = 2, PREP_UP2 = 4, PREP_PHASE2 = 8 };
 // Stages a conv/GEMM A operand: y = [silu]([groupnorm](cat(x0,x1))) -> fp16 hi(/lo).

@@ -240,8 +240,12 @@ struct Act {
   Half2Ptr raw16;  // optional fp16 hi/lo copy of the same values, written by the producing epilogue for consumers that
                    // read this tensor as a raw GEMM operand (skip 1x1 convs, upsample convs): no staging launch
   int n = 0, H = 0, W = 0, C = 0;
+  GnPart gn;       // GroupNorm statistics left by the producing GEMM (gn.slots > 0 once a producer filled them)
   size_t count() const { return (size_t)n * H * W * C; }
 };
+// channel bucket of the producer-side GroupNorm statistics: must divide the group size of every GroupNorm that reads the tensor,
+// alone or concatenated: 10 for the UNet widths (320/640/960/1280/1920/2560 -> groups of 10..80), C/32 for the VAE (128/256/512)
+static int gn_bucket_of(int C) { return C % 320 == 0 ? 10 : (C % 32 == 0 ? C / 32 : 0); }
 
 struct Fwd {
   Ctx& c;
@@ -282,6 +286,11 @@ struct Fwd {
     Act a;
     a.n = nb, a.H = H, a.W = W, a.C = C;
     a.p = c.work.get<float>(a.count());
+    a.gn.bucket = gn_bucket_of(C);
+    if (a.gn.bucket && c.opt_gn_epilogue) {
+      a.gn.cap = std::max(3 * ((H * W + 127) / 128), 160);
+      a.gn.buf = c.work.get<float>((size_t)nb * a.gn.cap * (C / a.gn.bucket) * 2);
+    }
     return a;
   }
   Half2Ptr half2(size_t count, bool lo) {
@@ -296,10 +305,28 @@ struct Fwd {
     ActOp a;
     a.n = nb, a.H = x0.H, a.W = x0.W, a.C = C;
     a.p = half2((size_t)nb * x0.H * x0.W * C, lo);
+    const int HW = x0.H * x0.W;
+    if (x0.gn.slots > 0 && (!x1 || (x1->gn.slots > 0 && x1->gn.bucket == x0.gn.bucket)) && (C / 32) % x0.gn.bucket == 0) {
+      GnSrc s0, s1;
+      auto src = [&](const Act& x, GnSrc& s) {
+        s.x = x.p, s.C = x.C, s.part = x.gn.buf, s.cap = x.gn.cap, s.slots = x.gn.slots;
+        if (x.gn.slots > 128) {  // large image: shorten the per-CTA fold with a first pass over groups of 64 slots
+          const int nbk = x.C / x.gn.bucket, s2 = gn_fold_slots(x.gn.slots);
+          float* folded = c.work.get<float>((size_t)nb * s2 * nbk * 2);
+          KernelScope ks(c, KC_GN_STATS, 0, (double)nb * x.gn.slots * nbk * 8.0);
+          gn_fold_launch(x.gn.buf, x.gn.cap, x.gn.slots, nbk, nb, folded, c.stream);
+          s.part = folded, s.cap = s2, s.slots = s2;
+        }
+      };
+      src(x0, s0);
+      if (x1) src(*x1, s1);
+      KernelScope ks(c, KC_PREP, 0, (double)nb * HW * C * (4.0 + 2.0 + (lo ? 2.0 : 0.0)));
+      gn_apply_launch(s0, s1, x0.gn.bucket, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, nw.eps, a.p, c.stream);
+      return a;
+    }
     SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
     unsigned int* tk = gn_tickets + (size_t)gn_slot * nb * 2;
     gn_slot++;
-    const int HW = x0.H * x0.W;
     float* part = c.work.get<float>(gn_fused_partial_floats(nb, HW));
     KernelScope ks(c, KC_PREP, 0, (double)nb * HW * C * (8.0 + 2.0 + (lo ? 2.0 : 0.0)));
     gn_fused_launch(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, nb, x0.H, x0.W, silu ? 1 : 0, nw.gamma, nw.beta, nw.eps,
@@ -348,7 +375,7 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
   Act h = f.act(x0.H, x0.W, c1.cout);
   {
     Epilogue ep;
-    ep.out_f32 = h.p;
+    ep.out_f32 = h.p, ep.gn = &h.gn;
     ep.bias = emb_bias ? emb_bias : c1.bias;
     run_gemm(c, G_CONV3, a, nullptr, c1.packed, passes, ep);
   }
@@ -363,7 +390,7 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
   }
   {
     Epilogue ep;
-    ep.out_f32 = out.p, ep.out_f16 = out.raw16;
+    ep.out_f32 = out.p, ep.out_f16 = out.raw16, ep.gn = &out.gn;
     ExtraK xk;
     if (merge) {
       xk.x0 = raw, xk.has_x1 = x1 != nullptr, xk.w = skip->packed;
@@ -472,22 +499,23 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   }
   // ---- GEGLU MLP: x += lin(x_a * gelu(gate))
   ln(s.ln3);
-  Half2Ptr g16 = f.half2((size_t)Mt * 4 * C, lo);
+  const int Pm = c.opt_mlp_passes ? c.opt_mlp_passes : P;  // pass policy of the MLP pair (DESIGN.md "precision")
+  Half2Ptr g16 = f.half2((size_t)Mt * 4 * C, Pm >= 2 || c.opt_precision >= 2);
   {
     Epilogue ep;
     ep.geglu = 1, ep.bias = s.geglu_bias, ep.out_f16 = g16;
-    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_geglu, P, ep);
+    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_geglu, Pm, ep);
   }
   Half2Ptr y16 = f.half2((size_t)Mt * C, lo);
   {
     Epilogue ep;
     ep.out_f32 = y, ep.residual = y, ep.bias = s.ff.bias, ep.out_f16 = y16;
-    run_gemm(c, G_LINEAR, f.rows_operand(g16, Mt, 4 * C), nullptr, s.ff.packed, P, ep);
+    run_gemm(c, G_LINEAR, f.rows_operand(g16, Mt, 4 * C), nullptr, s.ff.packed, Pm, ep);
   }
   // ---- proj_out + residual with the block input
   {
     Epilogue ep;
-    ep.out_f32 = out.p, ep.out_f16 = out.raw16, ep.residual = x.p, ep.bias = s.proj_out.bias;
+    ep.out_f32 = out.p, ep.out_f16 = out.raw16, ep.residual = x.p, ep.bias = s.proj_out.bias, ep.gn = &out.gn, ep.gn_rpi = HW;
     run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.proj_out.packed, P, ep);
   }
   c.work.off = mark;
@@ -580,7 +608,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
         const bool lo = b.conv.passes >= 2 || c.opt_precision >= 2;
         ActOp a = f.raw_operand(x0, nullptr, PREP_PHASE2, lo);
         Epilogue ep;
-        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias;
+        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias, ep.gn = &o.gn;
         run_gemm(c, G_CONV3_S2, a, nullptr, b.conv.packed, b.conv.passes, ep);
         c.work.off = mk;
         H /= 2, W /= 2;
@@ -613,7 +641,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
         const bool lo = b.conv.passes >= 2 || c.opt_precision >= 2;
         ActOp a = u.raw16.hi ? f.raw16_operand(u) : f.raw_operand(u, nullptr, 0, lo);
         Epilogue ep;
-        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias;
+        ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = b.conv.bias, ep.gn = &o.gn;
         run_gemm(c, G_CONV3_UP2, a, nullptr, b.conv.packed, b.conv.passes, ep);
         // `o` was allocated before mk, so releasing the temporaries keeps it alive
         c.work.off = mk;
@@ -716,7 +744,7 @@ static void run_vae_attention(Fwd& f, VaeAttnW& a, const Act& x, Act& out) {
   }
   {
     Epilogue ep;
-    ep.out_f32 = out.p, ep.residual = x.p, ep.bias = a.proj_out.bias;
+    ep.out_f32 = out.p, ep.residual = x.p, ep.bias = a.proj_out.bias, ep.gn = &out.gn, ep.gn_rpi = HW;
     run_gemm(c, G_LINEAR, f.rows_operand(o16, Mt, C), nullptr, a.proj_out.packed, P, ep);
   }
   c.work.off = mark;
@@ -759,7 +787,7 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
       const bool lo = db.up.passes >= 2 || c.opt_precision >= 2;
       ActOp a = x.raw16.hi ? f.raw16_operand(x) : f.raw_operand(x, nullptr, 0, lo);
       Epilogue ep;
-      ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = db.up.bias;
+      ep.out_f32 = o.p, ep.out_f16 = o.raw16, ep.bias = db.up.bias, ep.gn = &o.gn;
       run_gemm(c, G_CONV3_UP2, a, nullptr, db.up.packed, db.up.passes, ep);
       c.work.off = mk;
       x = o;
@@ -804,7 +832,7 @@ static void vae_encode(Fwd& f, const float* d_img4, int H, int W, float* d_laten
       const size_t mk = c.work.off;
       ActOp a = f.raw_operand(x, nullptr, PREP_PHASE2, true);
       Epilogue ep;
-      ep.out_f32 = o.p, ep.bias = eb.down.bias;
+      ep.out_f32 = o.p, ep.bias = eb.down.bias, ep.gn = &o.gn;
       run_gemm(c, G_CONV3_S2_PAD01, a, nullptr, eb.down.packed, eb.down.passes, ep);
       c.work.off = mk;
       x = o;

@@ -11,8 +11,12 @@
 
 namespace sdb {
 
-int g_pdl_late = 0;  // SDB_PDL=2: GEMMs release their dependents at epilogue start instead of at entry
-bool g_pdl_enabled = false;  // measured: PDL is ~3 % slower here (early CTAs compete with the draining kernel); SDB_PDL=1 enables it
+// Programmatic dependent launch (measured, tools/step_time.py, one process): off 155.3 ms/image; on with every kernel releasing its
+// dependents at entry 155.3 -> +1 % (early CTAs of the next kernel sit on the SMs while the GEMM still runs); on with the GEMMs
+// releasing them when their epilogue starts and loading their first weight tiles ahead of griddepcontrol.wait: -2.3 %.
+// SDB_PDL=0 disables, 1 = release at entry everywhere, 2 (default) = late release in the GEMMs.
+int g_pdl_late = 1;
+bool g_pdl_enabled = true;
 
 // ------------------------------------------------------------------ arena
 void Arena::init(size_t bytes) {
@@ -217,7 +221,9 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
               const ExtraK* xk) {
   ActOp a0 = a0in, a1;
   if (a1in) a1 = *a1in;
+  int gn_rpi = ep.gn_rpi, gn_nimg = 0;
   if (kind == G_CONV1) {  // a 1x1 conv over NHWC is a plain row-major GEMM
+    gn_rpi = a0.H * a0.W;
     a0.W = a0.n * a0.H * a0.W, a0.H = 1, a0.n = 1;
     if (a1in) a1.W = a1.n * a1.H * a1.W, a1.H = 1, a1.n = 1;
     kind = G_LINEAR;
@@ -341,6 +347,28 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     c.dbg_label = buf;
   }
 
+  // GroupNorm statistics of the output: needs every 32-row lane quarter inside one image, buckets that tile BN, slot room
+  GnPart* gn = ep.gn;
+  if (gn) {
+    int slots = m_tiles / p.tiles_n * split * phases_out;
+    bool geom = p.TN <= 4;
+    if (kind == G_LINEAR && gn_rpi > 0) {  // rows are tokens of gn_nimg images, gn_rpi rows each
+      const long long rows = (long long)a0.W;
+      geom = rows % gn_rpi == 0 && (gn_rpi % 128 == 0 || (128 % gn_rpi == 0 && gn_rpi >= 32));
+      gn_nimg = (int)(rows / gn_rpi);
+      slots = (gn_rpi >= 128 ? gn_rpi / 128 : 1) * split;
+    } else {
+      if (kind == G_LINEAR) geom = false;  // rows without an image size: the caller must say how many rows make an image
+      gn_rpi = 0;
+    }
+    const bool ok = gn->buf && gn->bucket > 0 && !ep.geglu && geom && BN >= 128 && BN % gn->bucket == 0 && w.N % gn->bucket == 0 &&
+                    slots <= gn->cap && c.opt_gn_epilogue;
+    gn->slots = ok ? slots : 0;
+    if (!ok) gn = nullptr;
+  }
+  p.gn_part = gn ? gn->buf : nullptr;
+  p.gn_cap = gn ? gn->cap : 0, p.gn_bucket = gn ? gn->bucket : 1;
+  p.gn_rpi = gn ? gn_rpi : 0, p.gn_nimg = gn_nimg;
   p.out_f32 = ep.out_f32;
   p.out_f16 = ep.out_f16.hi;
   p.out_f16_lo = ep.out_f16.lo;
@@ -350,6 +378,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.geglu = ep.geglu;
   p.act = ep.act;
   p.pdl_late = g_pdl_late;
+  p.prefetch_w = (g_pdl_enabled && c.opt_prefetch_w && m_tiles <= 4) ? 1 : 0;
   const int nout = ep.geglu ? w.N / 2 : w.N;
   p.ldc = ep.ldc ? ep.ldc : nout;
   p.ldc16 = ep.ldc16 ? ep.ldc16 : nout;
@@ -407,6 +436,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       maps.bx[0] = make_w_map(xk->w.p.hi, xk->w.K, xrows, bbox, xk->w.ld);
       maps.bx[1] = passes >= 3 ? make_w_map(xk->w.p.lo, xk->w.K, xrows, bbox, xk->w.ld) : maps.bx[0];
     }
+    p.gn_slot0 = phase * (m_tiles / p.tiles_n) * split;
     if (kind == G_CONV3_UP2) {
       const int a = phase >> 1, b = phase & 1;
       p.oa = a, p.ob = b;

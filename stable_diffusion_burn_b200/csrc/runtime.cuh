@@ -71,7 +71,16 @@ struct WeightOp {
 // (the VAE encoder's PaddedConv2d(0,1,0,1), autoencoder/mod.rs:229-236). Both read a 4-phase-plane operand.
 enum GemmKind : int { G_LINEAR = 0, G_CONV1 = 1, G_CONV3 = 2, G_CONV3_S2 = 3, G_CONV3_UP2 = 4, G_CONV3_S2_PAD01 = 5 };
 
+// GroupNorm statistics a producer leaves beside its output tensor (gemm_tc.cuh: gn_part): [n][cap][C / bucket][2] floats.
+// `slots` = partial slots really written per image (set by run_gemm; 0 = no statistics: the consumer computes its own).
+struct GnPart {
+  float* buf = nullptr;
+  int cap = 0, bucket = 0, slots = 0;
+};
+
 struct Epilogue {
+  GnPart* gn = nullptr;  // request statistics of the output (buf/cap/bucket preset by the caller)
+  int gn_rpi = 0;        // G_LINEAR over tokens only: rows per image (G_CONV1 fills it from the operand geometry)
   float* out_f32 = nullptr;
   Half2Ptr out_f16;
   const float* bias = nullptr;
@@ -111,6 +120,9 @@ struct Ctx {
   int opt_splitk_min_iters = 32, opt_splitk_chunk = 8;  // split-K: shortest K loop that is split, k-chunks kept per split
   int opt_skip_merge = 1; // ResBlock skip 1x1 conv folded into conv_out's K loop (needs raw16)
   int opt_raw16 = 1;      // epilogues also write the fp16 hi/lo copy a later raw-operand consumer needs (no staging launch)
+  int opt_mlp_passes = 0;   // 0: the transformer MLP (GEGLU + ff) follows its level's pass policy; 1: single fp16 pass everywhere
+  int opt_prefetch_w = 1;   // weight-bound GEMMs (<= 4 M tiles) prefetch their weight strip into L2 ahead of griddepcontrol.wait
+  int opt_gn_epilogue = 1;  // GroupNorm statistics produced by the GEMM epilogue that writes the tensor (no stats pass, no rendezvous)
   int opt_cluster = 1;    // CTA pairs issue cta_group::2 MMAs (256 x BN) wherever the M-tile count is even and K is not split
   // profiling
   bool profiling = false;

@@ -83,6 +83,30 @@ def test_groupnorm(ctx, n, c, H, W, silu):
     assert rel(out, ref.numpy()) < 5e-6
 
 
+# n, cin, H, W, cout, ksize: plain tiles (one image per tile), two / four images per tile (8x8, 8x4), split-K (small grid, long
+# K), a 1x1 conv over flattened tokens, a VAE width (bucket = group size), an awkward 12x12 map (masked tile rows)
+GN_FROM_GEMM = [(2, 320, 32, 32, 320, 3), (2, 1280, 8, 8, 1280, 3), (4, 640, 8, 4, 640, 3), (2, 1280, 16, 16, 640, 3),
+                (2, 320, 16, 16, 640, 1), (2, 640, 8, 8, 320, 1), (1, 512, 32, 32, 512, 3), (1, 256, 64, 64, 128, 3), (2, 320, 12, 12, 320, 3)]
+
+
+@pytest.mark.parametrize("n,cin,H,W,cout,k", GN_FROM_GEMM)
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm_from_gemm_statistics(ctx, n, cin, H, W, cout, k, silu):
+    """GroupNorm whose statistics come from the epilogue of the GEMM that wrote the tensor (no statistics pass)."""
+    x = rnd((n, cin, H, W), 51)
+    w = rnd((cout, cin, k, k), 52) / np.sqrt(cin * k * k)
+    b = rnd((cout,), 53) * 0.5 + 0.3  # a non-zero mean makes sum^2 / sumsq cancellation visible
+    g = 1 + 0.1 * rnd((cout,), 54); be = 0.1 * rnd((cout,), 55)
+    conv = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=k // 2)
+    ref = F.group_norm(conv, 32, torch.from_numpy(g).double(), torch.from_numpy(be).double(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    out, slots = ctx.test_conv_groupnorm(x, w, b, g, be, passes=3, silu=silu)
+    e = rel(out, ref.numpy())
+    print(f"GN from GEMM statistics n={n} {cin}->{cout} {H}x{W} k={k}: {slots} slots/image, rel L2 {e:.3e}")
+    assert slots > 0 and e < 3e-5
+
+
 @pytest.mark.parametrize("rows,c", [(100, 320), (64, 640), (33, 1280)])
 def test_layernorm(ctx, rows, c):
     x = rnd((rows, c), 31) * 2 - 0.3
