@@ -18,13 +18,17 @@
 
 namespace sdb {
 
-template <int DPAD, int NG>
+// VMN = false: V arrives transposed, V^T [d][keys] (K-major B operand of P.V: two boxes of [DPAD rows][64 keys]).
+// VMN = true : V arrives as the projection wrote it, V [keys][d] (MN-major B operand: DC boxes of [128 keys][64 channels]) —
+//              no transposing GEMM in front of the kernel.
+template <int DPAD, int NG, bool VMN = false>
 struct AttnCfg {
   static constexpr int DC = (DPAD + 63) / 64;                          // 64-wide chunks of the head dim
   static constexpr int Q_TILE = DC * 128 * 128;                         // [128 rows][64] x DC, 128 B rows
   static constexpr int K_BYTES = DC * 128 * 128;
-  static constexpr int V_CHUNK = ((DPAD * 128 + 1023) / 1024) * 1024;   // [DPAD rows][64 keys]
-  static constexpr int V_BYTES = 2 * V_CHUNK;
+  static constexpr int V_CHUNK = VMN ? 128 * 128 : ((DPAD * 128 + 1023) / 1024) * 1024;   // VMN: [128 keys][64 ch]; else [DPAD rows][64 keys]
+  static constexpr int V_BYTES = (VMN ? DC : 2) * V_CHUNK;
+  static constexpr int V_TX = VMN ? DC * 128 * 128 : 2 * DPAD * 128;    // bytes one V stage receives
   static constexpr int P_TILE = 2 * 128 * 128;                          // [128 rows][128 keys] fp16
   static constexpr int FIXED = NG * (Q_TILE + P_TILE) + 512 + 1024;
   static constexpr int ST = (FIXED + 2 * (K_BYTES + V_BYTES) <= 225 * 1024) ? 2 : 1;  // K/V pipeline stages
@@ -41,11 +45,11 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int DPAD, int NG>
+template <int DPAD, int NG, bool VMN>
 __global__ void __launch_bounds__(64 + 128 * NG, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const AttnParams p) {
-  using Cfg = AttnCfg<DPAD, NG>;
+  using Cfg = AttnCfg<DPAD, NG, VMN>;
   constexpr int DC = Cfg::DC, ST = Cfg::ST;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,17 +130,24 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           tma_load_2d(sK + st * Cfg::K_BYTES + c * 16384, &mk, &k_full[st], p.k_col0 + h * DPAD + c * 64,
                       s * p.k_rows_per_sample + j * 128);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], 2 * DPAD * 128);
+        mbar_expect_tx(&v_full[st], Cfg::V_TX);
+        if (VMN) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-          tma_load_2d(sV + st * Cfg::V_BYTES + c * Cfg::V_CHUNK, &mv, &v_full[st],
-                      s * p.k_rows_per_sample + j * 128 + c * 64, h * p.d);
+          for (int c = 0; c < DC; ++c)  // [128 keys][64 channels] boxes; channels past the head (or the matrix) are never multiplied
+            tma_load_2d(sV + st * Cfg::V_BYTES + c * Cfg::V_CHUNK, &mv, &v_full[st], p.v_col0 + h * DPAD + c * 64,
+                        s * p.k_rows_per_sample + j * 128);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(sV + st * Cfg::V_BYTES + c * Cfg::V_CHUNK, &mv, &v_full[st],
+                        s * p.k_rows_per_sample + j * 128 + c * 64, h * p.d);
+        }
       }
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
-    constexpr uint32_t idesc_o = make_idesc_f16(128, DPAD);
+    constexpr uint32_t idesc_o = make_idesc_f16(128, DPAD, false, /*b_mn_major=*/VMN);
     auto issue_qk = [&](int g, int j) {
       const int st = j % ST;
       if (g == 0) mbar_wait(&k_full[st], (j / ST) & 1);
@@ -170,9 +181,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint32_t poff = (kk / 4) * 16384 + (kk % 4) * 32;
-            const uint32_t voff = (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
-            umma_f16(tmem_base + NG * 128 + g * DPAD, make_sdesc_sw128(pa + poff), make_sdesc_sw128(va + voff), idesc_o,
-                     (j > 0 || kk > 0) ? 1u : 0u);
+            // K-major V^T: 16 keys = 32 bytes inside a 128-byte row; MN-major V: 16 keys = 16 rows of 128 bytes
+            const uint32_t voff = VMN ? kk * 2048 : (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
+            const uint64_t vdesc = VMN ? make_sdesc_sw128_mn(va + voff, Cfg::V_CHUNK) : make_sdesc_sw128(va + voff);
+            umma_f16(tmem_base + NG * 128 + g * DPAD, make_sdesc_sw128(pa + poff), vdesc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
           }
           if (g == NG - 1) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[g]);
@@ -306,15 +318,23 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   }
 }
 
+template <int DPAD, int NG, bool VMN>
+static void launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
+                         cudaStream_t st) {
+  constexpr int smem = AttnCfg<DPAD, NG, VMN>::SMEM;
+  static DeviceOnce once;
+  if (once.first())
+    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG, VMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
+  launch_k(attention_kernel<DPAD, NG, VMN>, grid, dim3(64 + 128 * NG), (size_t)smem, st, mq, mk, mv, p);
+}
 template <int DPAD, int NG>
 static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
                         cudaStream_t st) {
-  constexpr int smem = AttnCfg<DPAD, NG>::SMEM;
-  static DeviceOnce once;
-  if (once.first())
-    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
-  launch_k(attention_kernel<DPAD, NG>, grid, dim3(64 + 128 * NG), (size_t)smem, st, mq, mk, mv, p);
+  if (p.v_mn)
+    launch_attn2<DPAD, NG, true>(mq, mk, mv, p, st);
+  else
+    launch_attn2<DPAD, NG, false>(mq, mk, mv, p, st);
 }
 
 void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,

@@ -10,6 +10,8 @@ struct AttnParams {
   int q_rows_per_sample;      // row stride between samples in the Q matrix (and in the output)
   int k_rows_per_sample;      // row stride between samples in K (= column stride in V^T)
   int q_col0, k_col0;         // first column of head 0 inside the Q / K matrices
+  int v_mn, v_col0;           // v_mn = 1: V is a [keys][ldv] matrix (head h at columns v_col0 + h*dpad) consumed MN-major;
+                              // v_mn = 0: V^T [heads*d][ldv] (sample s at columns s*k_rows)
   const int* kvlen;           // [nb] valid keys per sample, or null (= Nk)
   int causal;                 // 1: query row i attends to keys 0..i only
   float scale;                // d^-1/2

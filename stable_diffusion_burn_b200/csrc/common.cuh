@@ -275,6 +275,17 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// Shared-memory matrix descriptor, MN-major operand, 128-byte swizzle: rows of the K dimension are 128 B (64 x 16-bit elements
+// contiguous along MN) apart, 8 K-rows form a 1024-byte swizzle atom (SBO), the next 64 MN elements start `lbo` bytes further.
+__device__ __forceinline__ uint64_t make_sdesc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes & 0x3FFFF) >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;    // SBO: 8 K-rows
+  d |= uint64_t(1) << 46;            // descriptor version (sm_100)
+  d |= uint64_t(2) << 61;            // SWIZZLE_128B
+  return d;
+}
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (one row per thread).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

@@ -113,12 +113,16 @@ __host__ __device__ constexpr int epilogue_warps() {
 // EPI selects what the epilogue does beside bias / residual / stores. It is a compile-time choice because the once-per-CTA
 // epilogue is instruction-issue bound: statistics code that is merely skipped at run time still cost ~0.5 us per launch.
 //   EPI_PLAIN  nothing more          EPI_GN   GroupNorm statistics of the output tensor (column sums per channel bucket)
-enum : int { EPI_PLAIN = 0, EPI_GN = 1 };
+//   EPI_LNS    LayerNorm row statistics of the output rows (partial sum / sum of squares per N-tile share)
+//   EPI_LNC    the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights: the normalisation is applied
+//              here as a rank-1 correction, out = rstd_r * (acc - mean_r * u_c) + v_c  (u = column sums of the folded weights,
+//              v = beta^T W + bias arrives as `bias`), from the row statistics the producer of A left (EPI_LNS)
+enum : int { EPI_PLAIN = 0, EPI_GN = 1, EPI_LNS = 2, EPI_LNC = 3 };
 
 template <int BN, int PASSES, int STAGES, int CG, int EPI>
 __global__ void __launch_bounds__(64 + 32 * epilogue_warps<BN, PASSES, STAGES, CG>(), min_ctas_per_sm<BN, PASSES, STAGES, CG>())
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  constexpr bool kGN = EPI == EPI_GN;
+  constexpr bool kGN = EPI == EPI_GN, kLNS = EPI == EPI_LNS, kLNC = EPI == EPI_LNC;
   using L = StageLayout<BN, PASSES, CG>;
   constexpr bool TWO = CG == 2;
   constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();  // epilogue warps
@@ -339,7 +343,25 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     int mr8[8], ao[8];
     float4 bvs[NCHUNK], ad[8];
     const float* ad_ptr = p.residual ? p.residual : p.rowbias;
+    const bool res_pair = p.res_hi != nullptr;  // the residual lives as an fp16 hi + lo pair (row stride ldc16)
     const bool plain = p.split_k == 1 && !p.geglu;
+    // EPI_LNC: mean / rstd of this lane's own accumulator row, from the partial row sums the producer of A left
+    float ln_mu = 0.f, ln_rs = 0.f;
+    float mu8[8], rs8[8];
+    float4 us[NCHUNK];
+    if constexpr (kLNC) {
+      if (m >= 0) {
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_in) + (size_t)m * p.ln_in_slots;
+        float sm = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_in_slots; ++i) {
+          const float2 v = sp[i];
+          sm += v.x, sq += v.y;
+        }
+        const float inv = 1.0f / (float)p.ln_C;
+        ln_mu = sm * inv;
+        ln_rs = rsqrtf(fmaxf(sq * inv - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
+    }
     {
       const bool use_res = p.residual != nullptr;
 #pragma unroll
@@ -348,8 +370,17 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int mr = __shfl_sync(0xffffffffu, m, rr);
         const int pnr = __shfl_sync(0xffffffffu, pn, rr);
         mr8[i] = mr;
-        ao[i] = use_res ? mr * p.ldc : pnr * p.N;
+        ao[i] = res_pair ? mr * p.ldc16 : (use_res ? mr * p.ldc : pnr * p.N);
         ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (kLNC) mu8[i] = __shfl_sync(0xffffffffu, ln_mu, rr), rs8[i] = __shfl_sync(0xffffffffu, ln_rs, rr);
+      }
+      if constexpr (kLNC) {
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+          const int col = col0 + half * 32 + j * CSTEP + cq;
+          us[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (half * 32 + j * CSTEP < BN && col < p.N) us[j] = *reinterpret_cast<const float4*>(p.ln_u + col);
+        }
       }
 #pragma unroll
       for (int j = 0; j < NCHUNK; ++j) {
@@ -359,7 +390,20 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
     auto issue_addends = [&](int col) {
-      if (ad_ptr == nullptr || col >= p.N) return;
+      if (col >= p.N) return;
+      if (res_pair) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (mr8[i] >= 0) {
+            const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + (unsigned)(ao[i] + col));
+            const uint2 l = *reinterpret_cast<const uint2*>(p.res_lo + (unsigned)(ao[i] + col));
+            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+            ad[i] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+          }
+        return;
+      }
+      if (ad_ptr == nullptr) return;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (mr8[i] >= 0) ad[i] = *reinterpret_cast<const float4*>(ad_ptr + (unsigned)(ao[i] + col));
@@ -462,6 +506,13 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
             if (p.rowbias) rb = *reinterpret_cast<const float4*>(p.rowbias + (size_t)qn * p.N + col);
             if (p.residual) rs = *reinterpret_cast<const float4*>(p.residual + (size_t)mr * p.ldc + col);
+            if (p.res_hi) {
+              const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + (size_t)mr * p.ldc16 + col);
+              const uint2 l = *reinterpret_cast<const uint2*>(p.res_lo + (size_t)mr * p.ldc16 + col);
+              const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+              const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+              rs = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+            }
             const float* wp = p.ws + (size_t)mr * p.N + col;
             const size_t zs = Mtot * p.N;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -541,12 +592,23 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         __syncwarp();
         const float4 bx = *reinterpret_cast<const float4*>(p.bias + col0 + c + cq);
         const float4 bg = *reinterpret_cast<const float4*>(p.bias + col0 + HB + c + cq);
+        float4 ux = make_float4(0.f, 0.f, 0.f, 0.f), ug = ux;
+        if constexpr (kLNC) {
+          ux = *reinterpret_cast<const float4*>(p.ln_u + col0 + c + cq);
+          ug = *reinterpret_cast<const float4*>(p.ln_u + col0 + HB + c + cq);
+        }
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub;
           const int mr = __shfl_sync(0xffffffffu, m, rr);
+          float rmu = 0.f, rrs = 1.f;
+          if constexpr (kLNC) rmu = __shfl_sync(0xffffffffu, ln_mu, rr), rrs = __shfl_sync(0xffffffffu, ln_rs, rr);
           if (mr >= 0) {
-            const float4 tx = unstage(tile_s, rr), tg = unstage(tile2_s, rr);
+            float4 tx = unstage(tile_s, rr), tg = unstage(tile2_s, rr);
+            if constexpr (kLNC) {
+              tx.x = rrs * (tx.x - rmu * ux.x), tx.y = rrs * (tx.y - rmu * ux.y), tx.z = rrs * (tx.z - rmu * ux.z), tx.w = rrs * (tx.w - rmu * ux.w);
+              tg.x = rrs * (tg.x - rmu * ug.x), tg.y = rrs * (tg.y - rmu * ug.y), tg.z = rrs * (tg.z - rmu * ug.z), tg.w = rrs * (tg.w - rmu * ug.w);
+            }
             float4 y;
             y.x = (tx.x + bx.x) * gelu_erf_fast(tg.x + bg.x);
             y.y = (tx.y + bx.y) * gelu_erf_fast(tg.y + bg.y);
@@ -560,6 +622,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     } else {
       constexpr int NCH = NCHUNK;  // column chunks per warp (the warps of a lane quarter interleave them)
       if (!pre_issued) issue_addends(col0 + half * 32 + cq);
+      float lrs[8], lrq[8];  // EPI_LNS: this lane's share of the row sums of its 8 rows
+#pragma unroll
+      for (int k = 0; k < 8; ++k) lrs[k] = 0.f, lrq[k] = 0.f;
+      (void)lrs, (void)lrq;
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         const int c = half * 32 + j * CSTEP;
@@ -571,6 +637,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           __syncwarp();
           const int col = col0 + c + cq;
           float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f), gsq = gsum;
+          (void)gsum, (void)gsq;
           if (col < p.N) {
             const uint32_t tl = tile_s + sub * TROW + cq * 4;
 #pragma unroll
@@ -587,7 +654,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 const int k = b4 * 4 + i;
                 if (mr8[k] < 0) continue;
                 float4 f = t[i];
+                if constexpr (kLNC) {  // LayerNorm folded in: rstd * (acc - mean * u) ; beta^T W + bias comes in through bvs
+                  f.x = rs8[k] * (f.x - mu8[k] * us[j].x), f.y = rs8[k] * (f.y - mu8[k] * us[j].y);
+                  f.z = rs8[k] * (f.z - mu8[k] * us[j].z), f.w = rs8[k] * (f.w - mu8[k] * us[j].w);
+                }
                 f.x += bvs[j].x + ad[k].x, f.y += bvs[j].y + ad[k].y, f.z += bvs[j].z + ad[k].z, f.w += bvs[j].w + ad[k].w;
+                if constexpr (kLNS) {
+                  lrs[k] += (f.x + f.y) + (f.z + f.w);
+                  lrq[k] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, lrq[k]))));
+                }
                 if constexpr (kGN) {
                   gsum.x += f.x, gsum.y += f.y, gsum.z += f.z, gsum.w += f.w;
                   gsq.x = fmaf(f.x, f.x, gsq.x), gsq.y = fmaf(f.y, f.y, gsq.y), gsq.z = fmaf(f.z, f.z, gsq.z), gsq.w = fmaf(f.w, f.w, gsq.w);
@@ -615,6 +690,25 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           __syncwarp();
           // the next chunk's addends travel while its accumulator columns are read and staged
           if (j + 1 < NCH && c + CSTEP < BN) issue_addends(col0 + c + CSTEP + cq);
+        }
+      }
+      if constexpr (kLNS) {
+        // the 8 lanes that share a row (same sub) fold their column groups in a fixed order; one of them publishes this warp's
+        // partial for the row: slot = (N tile, share of the chunks). The consumer adds the slots in index order.
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+          for (int o = 1; o <= 4; o <<= 1) {
+            lrs[k] += __shfl_xor_sync(0xffffffffu, lrs[k], o);
+            lrq[k] += __shfl_xor_sync(0xffffffffu, lrq[k], o);
+          }
+        }
+        if ((lane & 7) == 0) {
+          const int slot = blockIdx.y * EG + half;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (mr8[k] >= 0)
+              reinterpret_cast<float2*>(p.ln_out)[(size_t)mr8[k] * p.ln_slots + slot] = make_float2(lrs[k], lrq[k]);
         }
       }
       if constexpr (kGN) {
@@ -681,11 +775,21 @@ static void launch_epi(const GemmMaps& maps, const GemmParams& p, cudaStream_t s
 // the statistics-producing epilogues exist for the tile widths their tensors use (run_gemm checks with gemm_tc_supports_epi)
 template <int BN, int PASSES, int STAGES, int CG>
 static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
+  SDB_CHECK((p.gn_part != nullptr) + (p.ln_out != nullptr) + (p.ln_in != nullptr) <= 1, "one statistics role per launch");
   if constexpr (BN >= 128) {
     if (p.gn_part) return launch_epi<BN, PASSES, STAGES, CG, EPI_GN>(maps, p, stream);
   }
-  SDB_CHECK(!p.gn_part, "GroupNorm statistics are not built for this tile width");
+  if constexpr (BN == 160) {
+    if (p.ln_out) return launch_epi<BN, PASSES, STAGES, CG, EPI_LNS>(maps, p, stream);
+  }
+  if constexpr (BN == 128 || BN == 160) {
+    if (p.ln_in) return launch_epi<BN, PASSES, STAGES, CG, EPI_LNC>(maps, p, stream);
+  }
+  SDB_CHECK(!p.gn_part && !p.ln_out && !p.ln_in, "this statistics epilogue is not built for this tile width");
   launch_epi<BN, PASSES, STAGES, CG, EPI_PLAIN>(maps, p, stream);
+}
+bool gemm_tc_supports(int BN, int epi) {
+  return epi == EPI_PLAIN || (epi == EPI_GN && BN >= 128) || (epi == EPI_LNS && BN == 160) || (epi == EPI_LNC && (BN == 128 || BN == 160));
 }
 
 template <int BN, int PASSES, int CG>

@@ -51,6 +51,18 @@ struct GemmParams {
   int gn_cap, gn_bucket, gn_slot0;
   int gn_rpi, gn_nimg;     // flattened [rows][C] outputs (1x1 conv / Linear over tokens): rows per image (a multiple or a divisor
                            // of 128) and the image count; gn_rpi = 0: images follow the tile geometry (nimg, TN)
+  // LayerNorm folded into the GEMMs around it (no LayerNorm launch): the producer of the normalised tensor leaves per-row partial
+  // (sum, sum of squares) — ln_out [rows][ln_slots][2], slot = N tile * 2 + chunk share — and the consumer, whose weights carry
+  // gamma, applies out = rstd * (acc - mean * ln_u[c]) + bias[c] from ln_in [rows][ln_in_slots][2]
+  float* ln_out;
+  int ln_slots;
+  const float* ln_in;
+  int ln_in_slots, ln_C;
+  float ln_eps;
+  const float* ln_u;       // [N] column sums of the folded fp16 weights that this launch multiplies (hi, or hi + lo)
+  // residual kept as an fp16 hi + lo pair (row stride ldc16) instead of fp32: the transformer's residual stream
+  const __half* res_hi;
+  const __half* res_lo;
   float* ws;               // split-K workspace [split][M][N]
   unsigned int* tickets;   // split-K: one counter per output tile, all zero between launches (self-cleaning)
   // output pixel mapping: out row = ((n*OH + h*os + oa)*OW + w*os + ob)
@@ -62,6 +74,7 @@ struct GemmLaunch {
 };
 
 void gemm_tc_launch(const GemmMaps& maps, const GemmParams& p, int BN, int passes, cudaStream_t stream);
+bool gemm_tc_supports(int BN, int epi);  // epi: 0 plain, 1 GroupNorm statistics, 2 LayerNorm row statistics, 3 LayerNorm consume
 int gemm_tc_smem_bytes(int BN, int passes, int stages);
 
 }  // namespace sdb

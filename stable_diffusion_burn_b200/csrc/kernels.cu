@@ -1036,13 +1036,14 @@ void pack_conv_up2_launch(const float* w, int Cout, int Cin, Half2Ptr out, cudaS
 }
 
 __global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out, int ldw, int col0, __half* hi, __half* lo,
-                                   int row_offset) {
-  // tiled transpose [in][out] -> [out][in]
+                                   int row_offset, const float* __restrict__ in_scale) {
+  // tiled transpose [in][out] -> [out][in]; in_scale (optional) multiplies input feature i: a LayerNorm's gamma folded into
+  // the weights of the GEMM that consumes the normalised tensor
   __shared__ float tile[32][33];
   const int o0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = i0 + r, o = o0 + threadIdx.x;
-    tile[r][threadIdx.x] = (i < in && o < out) ? w[(size_t)i * ldw + col0 + o] : 0.f;
+    tile[r][threadIdx.x] = (i < in && o < out) ? w[(size_t)i * ldw + col0 + o] * (in_scale ? in_scale[i] : 1.0f) : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -1051,14 +1052,39 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int in, int out,
   }
 }
 void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st, int ldw,
-                        int col0) {
+                        int col0, const float* in_scale) {
   dim3 grid(ceil_div(out, 32), ceil_div(in, 32)), block(32, 8);
-  pack_linear_kernel<<<grid, block, 0, st>>>(w, in, out, ldw ? ldw : out, col0, dst.hi, dst.lo, row_offset);
+  pack_linear_kernel<<<grid, block, 0, st>>>(w, in, out, ldw ? ldw : out, col0, dst.hi, dst.lo, row_offset, in_scale);
+  SDB_CUDA(cudaGetLastError());
+}
+
+// row sums of a packed fp16 matrix [rows][K]: s_hi[r] = sum_k hi[r][k], s_full[r] = sum_k (hi + lo)[r][k] (fp32 accumulation
+// in a fixed order: one warp per row, lanes stride K, xor-tree) — the "u" vector of a LayerNorm folded into a GEMM: it must be
+// the sum of exactly the values the tensor cores multiply, or the mean would not cancel
+__global__ void __launch_bounds__(256) rowsum_f16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int rows,
+                                                         int K, float* __restrict__ s_hi, float* __restrict__ s_full) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float h = __half2float(hi[(size_t)row * K + k]);
+    a += h;
+    b += h + (lo ? __half2float(lo[(size_t)row * K + k]) : 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
+  if (lane == 0) {
+    if (s_hi) s_hi[row] = a;
+    if (s_full) s_full[row] = b;
+  }
+}
+void rowsum_f16_launch(Half2Ptr m, int rows, int K, float* s_hi, float* s_full, cudaStream_t st) {
+  rowsum_f16_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(m.hi, m.lo, rows, K, s_hi, s_full);
   SDB_CUDA(cudaGetLastError());
 }
 
 __global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ b, int in, int h4, int half_tile,
-                                  __half* hi, __half* lo, float* bias_packed) {
+                                  __half* hi, __half* lo, float* bias_packed, const float* __restrict__ in_scale) {
   // packed row pr in [0, 2*h4): tile j = pr / (2*half_tile); within tile q = pr % (2*half_tile);
   // q < half_tile -> x column j*half_tile + q ; else gate column h4 + j*half_tile + (q - half_tile)
   const long long total = (long long)2 * h4 * in;
@@ -1067,16 +1093,16 @@ __global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __re
     const int pr = int(idx / in);
     const int j = pr / (2 * half_tile), q = pr % (2 * half_tile);
     const int col = (q < half_tile) ? j * half_tile + q : h4 + j * half_tile + (q - half_tile);
-    split_store1(w[(size_t)i * (2 * h4) + col], hi, lo, (size_t)idx);
-    if (i == 0) bias_packed[pr] = b[col];
+    split_store1(w[(size_t)i * (2 * h4) + col] * (in_scale ? in_scale[i] : 1.0f), hi, lo, (size_t)idx);
+    if (i == 0 && bias_packed) bias_packed[pr] = b[col];
   }
 }
 void pack_geglu_launch(const float* w, const float* b, int in, int h4, int half_tile, Half2Ptr dst, float* bias_packed,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* in_scale) {
   const long long total = (long long)2 * h4 * in;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  pack_geglu_kernel<<<grid, 256, 0, st>>>(w, b, in, h4, half_tile, dst.hi, dst.lo, bias_packed);
+  pack_geglu_kernel<<<grid, 256, 0, st>>>(w, b, in, h4, half_tile, dst.hi, dst.lo, bias_packed, in_scale);
   SDB_CUDA(cudaGetLastError());
 }
 

@@ -105,11 +105,14 @@ void pack_conv_launch(const float* w, int Cout, int Cin, int ksize, Half2Ptr out
 void pack_conv_up2_launch(const float* w, int Cout, int Cin, Half2Ptr out, cudaStream_t st);
 // Linear [in][out] -> [out_row_offset + out][in] inside a packed matrix of row length ld (=in)
 // ldw/col0 select a column slice [col0, col0+out) of a source matrix with row stride ldw (0 -> out)
+// in_scale (optional, [in]): multiplies input feature i — a LayerNorm gamma folded into the consuming GEMM's weights
 void pack_linear_launch(const float* w, int in, int out, Half2Ptr dst, int row_offset, cudaStream_t st, int ldw = 0,
-                        int col0 = 0);
+                        int col0 = 0, const float* in_scale = nullptr);
+// per-row sums of a packed fp16 matrix [rows][K]: s_hi = sum hi, s_full = sum (hi + lo); either output may be null
+void rowsum_f16_launch(Half2Ptr m, int rows, int K, float* s_hi, float* s_full, cudaStream_t st);
 // GEGLU proj [in][2*H4] -> rows interleaved per 2*half-tile: tile j holds x rows j*half.. then gate rows
 void pack_geglu_launch(const float* w, const float* b, int in, int h4, int half_tile, Half2Ptr dst, float* bias_packed,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* in_scale = nullptr);
 // conv OIHW (Cout<=4, 3x3) -> fp32 [Cout][9][Cin]
 void pack_small_cout_launch(const float* w, int Cout, int Cin, float* out, cudaStream_t st);
 

@@ -93,16 +93,16 @@ static void pack_st(Ctx& c, SpatialTransformerW& s, int passes) {
   pack_norm(c, s.norm), pack_norm(c, s.ln1), pack_norm(c, s.ln2), pack_norm(c, s.ln3);
   pack_conv(c, s.proj_in), pack_conv(c, s.proj_out);
   const int hd = s.heads * s.dpad;
-  s.w_qk1.p = alloc_half2(c.packed, (size_t)2 * hd * s.c), s.w_qk1.N = 2 * hd, s.w_qk1.K = s.c;
-  pack_heads(c, s.attn1.query, s.heads, s.d, s.dpad, s.w_qk1.p, 0);
-  pack_heads(c, s.attn1.key, s.heads, s.d, s.dpad, s.w_qk1.p, hd);
-  pack_lin(c, s.attn1.value), s.w_v1 = s.attn1.value.packed;
+  s.w_qkv1.p = alloc_half2(c.packed, (size_t)3 * hd * s.c), s.w_qkv1.N = 3 * hd, s.w_qkv1.K = s.c;
+  pack_heads(c, s.attn1.query, s.heads, s.d, s.dpad, s.w_qkv1.p, 0);
+  pack_heads(c, s.attn1.key, s.heads, s.d, s.dpad, s.w_qkv1.p, hd);
+  pack_heads(c, s.attn1.value, s.heads, s.d, s.dpad, s.w_qkv1.p, 2 * hd);
   pack_lin(c, s.attn1.out), s.w_o1 = s.attn1.out.packed;
   s.w_q2.p = alloc_half2(c.packed, (size_t)hd * s.c), s.w_q2.N = hd, s.w_q2.K = s.c;
   pack_heads(c, s.attn2.query, s.heads, s.d, s.dpad, s.w_q2.p, 0);
-  s.w_k2.p = alloc_half2(c.packed, (size_t)hd * 768), s.w_k2.N = hd, s.w_k2.K = 768;
-  pack_heads(c, s.attn2.key, s.heads, s.d, s.dpad, s.w_k2.p, 0);
-  pack_lin(c, s.attn2.value), s.w_v2 = s.attn2.value.packed;
+  s.w_kv2.p = alloc_half2(c.packed, (size_t)2 * hd * 768), s.w_kv2.N = 2 * hd, s.w_kv2.K = 768;
+  pack_heads(c, s.attn2.key, s.heads, s.d, s.dpad, s.w_kv2.p, 0);
+  pack_heads(c, s.attn2.value, s.heads, s.d, s.dpad, s.w_kv2.p, hd);
   pack_lin(c, s.attn2.out), s.w_o2 = s.attn2.out.packed;
   s.w_geglu.p = alloc_half2(c.packed, (size_t)8 * s.c * s.c), s.w_geglu.N = 8 * s.c, s.w_geglu.K = s.c;
   s.geglu_bias = c.packed.get<float>((size_t)8 * s.c);
@@ -407,9 +407,7 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
 
 // per-layer K / V^T of the context tokens (constant over the DDIM steps)
 struct CtxKV {
-  __half* k = nullptr;   // [nb*Lpad][heads*dpad]
-  __half* vT = nullptr;  // [C][ldv]
-  int ldv = 0;
+  __half* kv = nullptr;  // [nb*Lpad][2*heads*dpad]: K | V of the context tokens, head-padded
 };
 struct CtxState {
   Half2Ptr ctx16;  // [nb*Lpad][768]
@@ -444,27 +442,18 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   };
   // ---- self attention: x += out(attn(q,k,v = LN1(x)))
   ln(s.ln1);
-  __half* qk = c.work.get<__half>((size_t)Mt * 2 * hd);
+  // one GEMM for q | k | v (head-padded columns); the attention kernel takes V as it is written here (MN-major operand)
+  __half* qkv = c.work.get<__half>((size_t)Mt * 3 * hd);
   {
     Epilogue ep;
-    ep.out_f16.hi = qk;
-    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_qk1, P, ep);
-  }
-  const int Mp = round_up((int)Mt, 32);  // token count padded for the N tiling; pad columns come out zero
-  __half* vT = c.work.get<__half>((size_t)C * Mp);
-  {
-    // V^T[C][tokens] = Wv^T[C][C] . LN(x)^T : weights as the A operand, tokens as the B operand
-    WeightOp tok;
-    tok.p = l16, tok.N = Mp, tok.rows = (int)Mt, tok.K = C;
-    Epilogue ep;
-    ep.out_f16.hi = vT;
-    run_gemm(c, G_LINEAR, f.rows_operand(s.w_v1.p, C, C), nullptr, tok, P, ep);
+    ep.out_f16.hi = qkv;
+    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_qkv1, P, ep);
   }
   {
     AttnOp at;
-    at.q = qk, at.ldq = 2 * hd, at.q_col0 = 0, at.q_rows = HW;
-    at.k = qk, at.ldk = 2 * hd, at.k_col0 = hd, at.k_rows = HW;
-    at.vT = vT, at.ldv = Mp;
+    at.q = qkv, at.ldq = 3 * hd, at.q_col0 = 0, at.q_rows = HW;
+    at.k = qkv, at.ldk = 3 * hd, at.k_col0 = hd, at.k_rows = HW;
+    at.vT = qkv, at.ldv = 3 * hd, at.v_mn = 1, at.v_col0 = 2 * hd;
     at.nb = f.nb, at.heads = s.heads, at.d = s.d, at.dpad = s.dpad, at.Nq = HW, at.Nk = HW;
     at.out = o16, at.ldo = C;
     run_attention(c, at);
@@ -485,8 +474,8 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   {
     AttnOp at;
     at.q = q2, at.ldq = hd, at.q_col0 = 0, at.q_rows = HW;
-    at.k = kv.k, at.ldk = hd, at.k_col0 = 0, at.k_rows = cs.Lpad;
-    at.vT = kv.vT, at.ldv = kv.ldv;
+    at.k = kv.kv, at.ldk = 2 * hd, at.k_col0 = 0, at.k_rows = cs.Lpad;
+    at.vT = kv.kv, at.ldv = 2 * hd, at.v_mn = 1, at.v_col0 = hd;
     at.nb = f.nb, at.heads = s.heads, at.d = s.d, at.dpad = s.dpad, at.Nq = HW, at.Nk = cs.Lpad;
     at.kvlen = cs.kvlen;
     at.out = o16, at.ldo = C;
@@ -539,20 +528,11 @@ static void prepare_context(Fwd& f, const float* d_ctx /*[nb][Lpad][768] zero pa
     SpatialTransformerW& s = *m.sts[i];
     const int hd = s.heads * s.dpad;
     CtxKV& kv = cs.kv[i];
-    kv.k = c.work.get<__half>((size_t)rows * hd);
-    kv.ldv = (int)rows;
-    kv.vT = c.work.get<__half>((size_t)s.c * rows);
+    kv.kv = c.work.get<__half>((size_t)rows * 2 * hd);
     {
       Epilogue ep;
-      ep.out_f16.hi = kv.k;
-      run_gemm(c, G_LINEAR, f.rows_operand(cs.ctx16, rows, 768), nullptr, s.w_k2, 3, ep);
-    }
-    {
-      WeightOp tok;
-      tok.p = cs.ctx16, tok.N = (int)rows, tok.K = 768;
-      Epilogue ep;
-      ep.out_f16.hi = kv.vT;
-      run_gemm(c, G_LINEAR, f.rows_operand(s.w_v2.p, s.c, 768), nullptr, tok, 3, ep);
+      ep.out_f16.hi = kv.kv;
+      run_gemm(c, G_LINEAR, f.rows_operand(cs.ctx16, rows, 768), nullptr, s.w_kv2, 3, ep);
     }
   }
 }
@@ -1062,7 +1042,7 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
   int64_t graph_launches = 0;
   if (use_graph) {
     for (auto& g : m.graphs)
-      if (g.key == key && g.io[0] == (void*)xb && g.io[1] == (void*)eps && g.io[2] == (void*)cs.kv[0].k) exec = g.exec,
+      if (g.key == key && g.io[0] == (void*)xb && g.io[1] == (void*)eps && g.io[2] == (void*)cs.kv[0].kv) exec = g.exec,
           graph_launches = (int64_t)(intptr_t)g.io[3];
     if (!exec) {
       // warm-up pass outside capture (sets kernel attributes), then capture
@@ -1087,7 +1067,7 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
       Model::GraphEntry ge;
       ge.key = key, ge.exec = exec;
       memset(ge.io, 0, sizeof(ge.io));
-      ge.io[0] = xb, ge.io[1] = eps, ge.io[2] = cs.kv[0].k, ge.io[3] = (void*)(intptr_t)graph_launches;
+      ge.io[0] = xb, ge.io[1] = eps, ge.io[2] = cs.kv[0].kv, ge.io[3] = (void*)(intptr_t)graph_launches;
       m.graphs.push_back(ge);
     }
   }
@@ -1278,11 +1258,10 @@ void model_clip_forward_host(Ctx& c, const int* tokens, int n, int L, float* out
 // ================================================================================ attention unit-test entry
 void model_test_attention(Ctx& c, const float* q, const float* k, const float* v, int n, int Nq, int Nk, int C, int heads,
                           float* out) {
-  // stages q/k/v exactly as the SpatialTransformer does: head-padded q|k rows, V^T [C][n*Nk]
+  // stages q / k|v exactly as the SpatialTransformer does: head-padded rows, V row-major beside K (consumed MN-major)
   const int d = C / heads, dpad = (d % 16 == 0) ? d : (d + 15) / 16 * 16, hd = heads * dpad;
   const int Nkp = round_up(Nk, 8);
-  std::vector<__half> hq((size_t)n * Nq * hd, __float2half(0.f)), hk((size_t)n * Nkp * hd, __float2half(0.f)),
-      hv((size_t)C * n * Nkp, __float2half(0.f));
+  std::vector<__half> hq((size_t)n * Nq * hd, __float2half(0.f)), hkv((size_t)n * Nkp * 2 * hd, __float2half(0.f));
   for (int s = 0; s < n; ++s)
     for (int i = 0; i < Nq; ++i)
       for (int h = 0; h < heads; ++h)
@@ -1292,25 +1271,23 @@ void model_test_attention(Ctx& c, const float* q, const float* k, const float* v
     for (int i = 0; i < Nk; ++i)
       for (int h = 0; h < heads; ++h)
         for (int j = 0; j < d; ++j) {
-          hk[((size_t)s * Nkp + i) * hd + h * dpad + j] = __float2half(k[((size_t)s * Nk + i) * C + h * d + j]);
-          hv[(size_t)(h * d + j) * n * Nkp + (size_t)s * Nkp + i] = __float2half(v[((size_t)s * Nk + i) * C + h * d + j]);
+          hkv[((size_t)s * Nkp + i) * 2 * hd + h * dpad + j] = __float2half(k[((size_t)s * Nk + i) * C + h * d + j]);
+          hkv[((size_t)s * Nkp + i) * 2 * hd + hd + h * dpad + j] = __float2half(v[((size_t)s * Nk + i) * C + h * d + j]);
         }
   __half* dq = c.work.get<__half>(hq.size());
-  __half* dk = c.work.get<__half>(hk.size());
-  __half* dv = c.work.get<__half>(hv.size());
+  __half* dkv = c.work.get<__half>(hkv.size());
   Half2Ptr o16;
   o16.hi = c.work.get<__half>((size_t)n * Nq * C);
   o16.lo = c.work.get<__half>((size_t)n * Nq * C);
   int* dlen = c.work.get<int>(n);
   std::vector<int> lens(n, Nk);
   SDB_CUDA(cudaMemcpyAsync(dq, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice, c.stream));
-  SDB_CUDA(cudaMemcpyAsync(dk, hk.data(), hk.size() * 2, cudaMemcpyHostToDevice, c.stream));
-  SDB_CUDA(cudaMemcpyAsync(dv, hv.data(), hv.size() * 2, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(dkv, hkv.data(), hkv.size() * 2, cudaMemcpyHostToDevice, c.stream));
   SDB_CUDA(cudaMemcpyAsync(dlen, lens.data(), n * 4, cudaMemcpyHostToDevice, c.stream));
   AttnOp at;
   at.q = dq, at.ldq = hd, at.q_rows = Nq;
-  at.k = dk, at.ldk = hd, at.k_rows = Nkp;
-  at.vT = dv, at.ldv = n * Nkp;
+  at.k = dkv, at.ldk = 2 * hd, at.k_rows = Nkp;
+  at.vT = dkv, at.ldv = 2 * hd, at.v_mn = 1, at.v_col0 = hd;
   at.nb = n, at.heads = heads, at.d = d, at.dpad = dpad, at.Nq = Nq, at.Nk = Nkp;
   at.kvlen = dlen;
   at.out = o16, at.ldo = C;

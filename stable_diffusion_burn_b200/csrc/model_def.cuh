@@ -49,14 +49,17 @@ struct SpatialTransformerW {
   AttnW attn1, attn2;
   LinW geglu, ff;
   // fused / re-laid-out projections
-  WeightOp w_qk1;      // [2*heads*dpad][c]   self-attention q|k, head-padded
-  WeightOp w_v1;       // [c][c]              value, used as the A operand -> V^T
+  WeightOp w_qkv1;     // [3*heads*dpad][c]   self-attention q|k|v, head-padded (V is consumed MN-major by the attention kernel)
   WeightOp w_q2;       // [heads*dpad][c]     cross-attention q
-  WeightOp w_k2;       // [heads*dpad][768]   cross-attention k (context)
-  WeightOp w_v2;       // [c][768]            cross-attention v as the A operand -> V^T
+  WeightOp w_kv2;      // [2*heads*dpad][768] cross-attention k|v (context), head-padded
   WeightOp w_o1, w_o2; // [c][heads*d] out projections (un-padded input)
   WeightOp w_geglu;    // [8c][c] tile-interleaved x|gate
   float* geglu_bias = nullptr;  // packed order
+  // LayerNorm folded into the consuming GEMMs (w_qkv1 <- ln1, w_q2 <- ln2, w_geglu <- ln3: gamma is inside the packed weights):
+  // u = column sums of the packed fp16 weights (hi / hi + lo), v = beta^T W (+ bias)
+  float *u_qkv_hi = nullptr, *u_qkv_full = nullptr, *v_qkv = nullptr;
+  float *u_q2_hi = nullptr, *u_q2_full = nullptr, *v_q2 = nullptr;
+  float *u_geglu_hi = nullptr, *u_geglu_full = nullptr, *v_geglu = nullptr;
   int passes = 1;
 };
 enum BlockKind : int { BK_CONV = 0, BK_DOWN, BK_R, BK_RT, BK_RU, BK_RTU };

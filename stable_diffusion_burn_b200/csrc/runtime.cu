@@ -187,13 +187,15 @@ void run_attention(Ctx& c, const AttnOp& a) {
   p.nb = a.nb, p.heads = a.heads, p.d = a.d, p.dpad = a.dpad, p.Nq = a.Nq, p.Nk = a.Nk;
   p.q_rows_per_sample = a.q_rows, p.k_rows_per_sample = a.k_rows;
   p.q_col0 = a.q_col0, p.k_col0 = a.k_col0;
+  p.v_mn = a.v_mn, p.v_col0 = a.v_col0;
   p.kvlen = a.kvlen;
   p.causal = a.causal;
   p.scale = (float)(1.0 / std::sqrt((double)a.d));
   p.out_hi = a.out.hi, p.out_lo = a.out.lo, p.ldo = a.ldo;
   const CUtensorMap mq = make_mat_map(a.q, a.ldq, (long long)a.nb * a.q_rows, 128);
   const CUtensorMap mk = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
-  const CUtensorMap mv = make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
+  const CUtensorMap mv = a.v_mn ? make_mat_map(a.vT, a.ldv, (long long)a.nb * a.k_rows, 128)
+                                : make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
   const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
   if (c.debug_sync || c.profiling) {
     char buf[200];
@@ -318,13 +320,18 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     BN = 128;
   else
     BN = 64;
+  if (ep.ln_out) {
+    SDB_CHECK(w.N % 160 == 0 && !ep.geglu, "LayerNorm statistics need an output width that tiles by 160");
+    BN = 160;
+  }
+  if (ep.ln_in) SDB_CHECK(BN == 128 || BN == 160, "LayerNorm-consuming GEMM: tile width");
   const int n_tiles = (w.N + BN - 1) / BN;
 
 
   // split-K when the grid cannot fill the machine and the K loop is long
   const int iters = p.num_taps * p.kc + p.xkc;
   int split = 1;
-  if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu) {
+  if (c.opt_splitk && kind != G_CONV3_UP2 && !ep.geglu && !ep.ln_out && !ep.ln_in) {
     const int ctas = m_tiles * n_tiles;
     if (ctas <= 74 && iters >= c.opt_splitk_min_iters) {
       // floor: ctas*split must stay within ONE wave of the 148 SMs (a 2-wave grid costs 2x, see profiles/r1);
@@ -369,6 +376,13 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.gn_part = gn ? gn->buf : nullptr;
   p.gn_cap = gn ? gn->cap : 0, p.gn_bucket = gn ? gn->bucket : 1;
   p.gn_rpi = gn ? gn_rpi : 0, p.gn_nimg = gn_nimg;
+  p.ln_out = ep.ln_out, p.ln_slots = ln_slots(w.N);
+  p.ln_in = ep.ln_in, p.ln_in_slots = ep.ln_in_slots, p.ln_C = ep.ln_C, p.ln_eps = ep.ln_eps;
+  p.ln_u = passes >= 3 ? ep.ln_u_full : ep.ln_u_hi;
+  SDB_CHECK(!ep.ln_in || (p.ln_u && ep.ln_in_slots > 0 && ep.ln_C == w.K && kind == G_LINEAR), "LayerNorm-consuming GEMM: arguments");
+  SDB_CHECK(!ep.ln_out || kind == G_LINEAR, "LayerNorm statistics: rows must be tokens");
+  p.res_hi = ep.residual16.hi, p.res_lo = ep.residual16.lo;
+  SDB_CHECK(!ep.residual16.hi || (ep.residual16.lo && !ep.residual && !ep.rowbias), "fp16-pair residual: needs both halves, excludes the fp32 residual / row bias");
   p.out_f32 = ep.out_f32;
   p.out_f16 = ep.out_f16.hi;
   p.out_f16_lo = ep.out_f16.lo;

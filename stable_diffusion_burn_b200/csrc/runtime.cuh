@@ -79,6 +79,15 @@ struct GnPart {
 };
 
 struct Epilogue {
+  // LayerNorm folded into the surrounding GEMMs (gemm_tc.cuh): producer side leaves row statistics of its output, consumer
+  // side (weights carry gamma, `bias` carries beta^T W + b) normalises in its epilogue
+  float* ln_out = nullptr;         // [rows][ln_slots(N)][2]
+  const float* ln_in = nullptr;    // [rows][ln_in_slots][2]
+  int ln_in_slots = 0, ln_C = 0;
+  float ln_eps = 1e-5f;
+  const float* ln_u_hi = nullptr;  // column sums of the hi halves of the folded weights (1- and 2-pass products)
+  const float* ln_u_full = nullptr;  // column sums of hi + lo (3-pass products)
+  Half2Ptr residual16;             // residual as an fp16 hi + lo pair (row stride ldc16) instead of `residual`
   GnPart* gn = nullptr;  // request statistics of the output (buf/cap/bucket preset by the caller)
   int gn_rpi = 0;        // G_LINEAR over tokens only: rows per image (G_CONV1 fills it from the operand geometry)
   float* out_f32 = nullptr;
@@ -182,8 +191,9 @@ struct AttnOp {
   int ldq = 0, q_col0 = 0, q_rows = 0;
   const __half* k = nullptr;
   int ldk = 0, k_col0 = 0, k_rows = 0;
-  const __half* vT = nullptr;
+  const __half* vT = nullptr;  // V^T [heads*d][ldv], or with v_mn = 1 the row-major V [nb*k_rows][ldv] (head-padded like k)
   int ldv = 0;
+  int v_mn = 0, v_col0 = 0;
   int nb = 1, heads = 8, d = 0, dpad = 0, Nq = 0, Nk = 0;
   const int* kvlen = nullptr;
   int causal = 0;  // 1: key j visible to query i only if j <= i (CLIP, src/backend.rs:130-139)
@@ -191,6 +201,8 @@ struct AttnOp {
   int ldo = 0;
 };
 void run_attention(Ctx& c, const AttnOp& a);
+// partial-sum slots per row that a LayerNorm-statistics producer of width N writes (N tiles of 160 x 2 chunk shares)
+inline int ln_slots(int N) { return ((N + 159) / 160) * 2; }
 
 const char* kernel_class_name(int cls);
 
