@@ -163,6 +163,13 @@ int sdb_test_gemm_ex(sdb_ctx* ctx, const float* a, const float* w, const float* 
 /* conv2d NCHW fp32 in/out through the implicit-GEMM path (3x3 pad 1 stride 1|2, or 1x1). */
 int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* bias, int n, int cin, int H,
                     int W, int cout, int ksize, int stride, int upsample, int passes, float* y);
+/* The LayerNorm-free TransformerBlock chain in isolation (unet/mod.rs:521-527): y = a w0 + b0 (+ a2 w0 + b0 accumulated in place
+ * on the fp16 hi/lo residual pair; a2 may be NULL) with row statistics from the producing epilogue, then
+ * out = LayerNorm(y; gamma, beta) w1 + b1 with the LayerNorm folded into the consuming GEMM (gamma in the weights, rank-1
+ * correction in the epilogue); geglu = 1: w1 = [C][x | gate], out [M, N/2] = x * gelu(gate). C a multiple of 160. */
+int sdb_test_ln_fold(sdb_ctx* ctx, const float* a, const float* a2, const float* w0, const float* b0, const float* gamma,
+                     const float* beta, const float* w1, const float* b1, int M, int K0, int C, int N, int passes, int geglu,
+                     float* out);
 /* conv (3x3 pad 1 or 1x1) whose epilogue also leaves the GroupNorm statistics of its output, followed by the apply-only
  * GroupNorm(+SiLU) that consumes them (the ResBlock's conv_in -> norm_out -> SiLU chain, unet/mod.rs:716-725). NCHW fp32 in/out;
  * *slots = partial-statistics slots per image the GEMM wrote (> 0). */

@@ -68,6 +68,8 @@ SIGNATURES = [
     ("sdb_test_linear", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     ("sdb_test_conv2d", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, _f32p]),
+    ("sdb_test_ln_fold", C.c_int, [_ctx, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, _f32p]),
     ("sdb_test_conv_groupnorm", C.c_int, [_ctx, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int)]),
     ("sdb_test_groupnorm", C.c_int, [_ctx, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
@@ -309,6 +311,17 @@ class Context:
         self.check(self.lib.sdb_test_conv2d(self.h, ptr(x), ptr(w), ptr(b) if b is not None else None, n, cin, H, W, cout,
                                             k, stride, upsample, passes, ptr(y)))
         return y
+
+    def test_ln_fold(self, a, w0, b0, gamma, beta, w1, b1=None, a2=None, passes=3, geglu=False):
+        a, w0, b0, gamma, beta, w1 = (f32(v) for v in (a, w0, b0, gamma, beta, w1))
+        b1 = f32(b1) if b1 is not None else None
+        a2 = f32(a2) if a2 is not None else None
+        M, K0 = a.shape; Cc = w0.shape[1]; N = w1.shape[1]
+        out = np.empty((M, N // 2 if geglu else N), np.float32)
+        self.check(self.lib.sdb_test_ln_fold(self.h, ptr(a), ptr(a2) if a2 is not None else None, ptr(w0), ptr(b0), ptr(gamma),
+                                             ptr(beta), ptr(w1), ptr(b1) if b1 is not None else None, M, K0, Cc, N, passes,
+                                             1 if geglu else 0, ptr(out)))
+        return out
 
     def test_conv_groupnorm(self, x, w, bias, gamma, beta, passes=3, silu=False):
         x = f32(x); w = f32(w); bias = f32(bias); gamma = f32(gamma); beta = f32(beta)

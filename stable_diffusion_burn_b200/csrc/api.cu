@@ -620,6 +620,71 @@ int sdb_test_conv2d(sdb_ctx* ctx, const float* x, const float* w, const float* b
   API_END
 }
 
+int sdb_test_ln_fold(sdb_ctx* ctx, const float* a, const float* a2, const float* w0, const float* b0, const float* gamma,
+                     const float* beta, const float* w1, const float* b1, int M, int K0, int C, int N, int passes, int geglu,
+                     float* out) {
+  API_BEGIN(ctx)
+  c.work.reset();
+  SDB_CHECK(C % 160 == 0 && K0 % 64 == 0 && (!geglu || (N % 128 == 0 && b1)), "ln_fold test shapes");
+  auto up = [&](const float* h, size_t cnt) {
+    float* d = c.work.get<float>(cnt);
+    SDB_CUDA(cudaMemcpyAsync(d, h, sizeof(float) * cnt, cudaMemcpyHostToDevice, c.stream));
+    return d;
+  };
+  auto h2 = [&](size_t cnt) { return Half2Ptr{c.work.get<__half>(cnt), c.work.get<__half>(cnt)}; };
+  float *d_w0 = up(w0, (size_t)K0 * C), *d_b0 = up(b0, C), *d_g = up(gamma, C), *d_be = up(beta, C), *d_w1 = up(w1, (size_t)C * N);
+  float* d_b1 = b1 ? up(b1, N) : nullptr;
+  WeightOp W0;
+  W0.p = h2((size_t)C * K0), W0.N = C, W0.K = K0;
+  pack_linear_launch(d_w0, K0, C, W0.p, 0, c.stream);
+  // consumer weights with gamma folded in, u / v vectors (the same recipe as pack_st)
+  WeightOp W1;
+  W1.p = h2((size_t)N * C), W1.N = N, W1.K = C;
+  Half2Ptr scratch = h2((size_t)N * C);
+  float *u_hi = c.work.get<float>(N), *u_full = c.work.get<float>(N), *v = c.work.get<float>(N), *bp = c.work.get<float>(N);
+  if (geglu) {
+    pack_geglu_launch(d_w1, d_b1, C, N / 2, 64, W1.p, bp, c.stream, d_g);
+    pack_geglu_launch(d_w1, d_b1, C, N / 2, 64, scratch, nullptr, c.stream, d_be);
+  } else {
+    pack_linear_launch(d_w1, C, N, W1.p, 0, c.stream, 0, 0, d_g);
+    pack_linear_launch(d_w1, C, N, scratch, 0, c.stream, 0, 0, d_be);
+  }
+  rowsum_f16_launch(W1.p, N, C, u_hi, u_full, c.stream);
+  rowsum_f16_launch(scratch, N, C, nullptr, v, c.stream);
+  if (geglu) add_vec_launch(v, bp, N, v, c.stream);
+  else if (d_b1) add_vec_launch(v, d_b1, N, v, c.stream);
+  // producer(s): y = a w0 + b0 (+ a2 w0 + b0 accumulated in place onto the fp16 pair), leaving row statistics
+  Half2Ptr y16 = h2((size_t)M * C);
+  const int ls = ln_slots(C);
+  float* st = c.work.get<float>((size_t)M * ls * 2);
+  for (int pass = 0; pass < (a2 ? 2 : 1); ++pass) {
+    float* d_a = up(pass ? a2 : a, (size_t)M * K0);
+    ActOp A;
+    A.p = h2((size_t)M * K0), A.W = M, A.C = K0;
+    convert_f16_launch(d_a, (long long)M * K0, A.p, c.stream);
+    Epilogue ep;
+    ep.out_f16 = y16, ep.bias = d_b0, ep.ln_out = st;
+    if (pass) ep.residual16 = y16;
+    run_gemm(c, G_LINEAR, A, nullptr, W0, 3, ep);
+  }
+  const int Nout = geglu ? N / 2 : N;
+  Half2Ptr o16 = h2((size_t)M * Nout);
+  {
+    ActOp Y;
+    Y.p = y16, Y.W = M, Y.C = C;
+    Epilogue ep;
+    ep.out_f16 = o16, ep.geglu = geglu ? 1 : 0;
+    ep.ln_in = st, ep.ln_in_slots = ls, ep.ln_C = C, ep.ln_eps = 1e-5f, ep.ln_u_hi = u_hi, ep.ln_u_full = u_full, ep.bias = v;
+    run_gemm(c, G_LINEAR, Y, nullptr, W1, passes, ep);
+  }
+  std::vector<__half> hi((size_t)M * Nout), lo((size_t)M * Nout);
+  SDB_CUDA(cudaMemcpyAsync(hi.data(), o16.hi, hi.size() * 2, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(lo.data(), o16.lo, lo.size() * 2, cudaMemcpyDeviceToHost, c.stream));
+  SDB_CUDA(cudaStreamSynchronize(c.stream));
+  for (size_t i = 0; i < hi.size(); ++i) out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+  API_END
+}
+
 int sdb_test_conv_groupnorm(sdb_ctx* ctx, const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
                             int n, int cin, int H, int W, int cout, int ksize, int passes, int silu, float* y, int* used_epilogue_stats) {
   API_BEGIN(ctx)

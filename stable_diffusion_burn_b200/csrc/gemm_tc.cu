@@ -104,10 +104,14 @@ __host__ __device__ constexpr int min_ctas_per_sm() {
 }
 
 // Epilogue warps (a multiple of 4: one group per TMEM lane quarter). Measured: 16 warps on the SM-owning variants do not
-// shorten the epilogue (6.4k vs 6.7k cycles for 128 x 160) and lengthen the tail, so every variant uses 8.
+// shorten the epilogue (6.4k vs 6.7k cycles for 128 x 160) and lengthen the tail, so those use 8. The variants that share an
+// SM between two CTAs use 4: with 8 they were capped at 96 registers per thread and spilled 140-950 bytes per thread, and with
+// the shared-memory carve-out at its maximum L1 holds nothing, so every spill access is an L2 round trip (ncu on the q|k|v
+// projection: 225 K local loads + 152 K local stores, 48 MB of local traffic for 19 MB of output, long-scoreboard the top stall).
+// 4 warps (192 threads per CTA) leave 170 registers per thread: no spills.
 template <int BN, int PASSES, int STAGES, int CG>
 __host__ __device__ constexpr int epilogue_warps() {
-  return 8;
+  return min_ctas_per_sm<BN, PASSES, STAGES, CG>() == 2 ? 4 : 8;
 }
 
 // EPI selects what the epilogue does beside bias / residual / stores. It is a compile-time choice because the once-per-CTA
@@ -390,6 +394,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
     auto issue_addends = [&](int col) {
+      if constexpr (kLNC) return;  // a LayerNorm-consuming GEMM has neither residual nor row bias (run_gemm checks): no registers for them
       if (col >= p.N) return;
       if (res_pair) {
 #pragma unroll
@@ -658,7 +663,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                   f.x = rs8[k] * (f.x - mu8[k] * us[j].x), f.y = rs8[k] * (f.y - mu8[k] * us[j].y);
                   f.z = rs8[k] * (f.z - mu8[k] * us[j].z), f.w = rs8[k] * (f.w - mu8[k] * us[j].w);
                 }
-                f.x += bvs[j].x + ad[k].x, f.y += bvs[j].y + ad[k].y, f.z += bvs[j].z + ad[k].z, f.w += bvs[j].w + ad[k].w;
+                if constexpr (kLNC)
+                  f.x += bvs[j].x, f.y += bvs[j].y, f.z += bvs[j].z, f.w += bvs[j].w;
+                else
+                  f.x += bvs[j].x + ad[k].x, f.y += bvs[j].y + ad[k].y, f.z += bvs[j].z + ad[k].z, f.w += bvs[j].w + ad[k].w;
                 if constexpr (kLNS) {
                   lrs[k] += (f.x + f.y) + (f.z + f.w);
                   lrq[k] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, lrq[k]))));
@@ -704,11 +712,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           }
         }
         if ((lane & 7) == 0) {
-          const int slot = blockIdx.y * EG + half;
+          // two slots per N tile whatever the warp count (the consumer's slot count is a function of N alone)
+          const int slot = blockIdx.y * 2 + half;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            if (mr8[k] >= 0)
-              reinterpret_cast<float2*>(p.ln_out)[(size_t)mr8[k] * p.ln_slots + slot] = make_float2(lrs[k], lrq[k]);
+            if (mr8[k] >= 0) {
+              float2* d = reinterpret_cast<float2*>(p.ln_out) + (size_t)mr8[k] * p.ln_slots + slot;
+              d[0] = make_float2(lrs[k], lrq[k]);
+              if (EG == 1) d[1] = make_float2(0.f, 0.f);
+            }
         }
       }
       if constexpr (kGN) {

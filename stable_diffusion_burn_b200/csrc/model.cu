@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 
 #include "model_def.cuh"
 
@@ -72,9 +73,10 @@ static void pack_norm(Ctx& c, NormW& n) {
 }
 
 // [rows = heads*dpad][in]: head h occupies rows h*dpad .. h*dpad+d (pad rows stay zero)
-static void pack_heads(Ctx& c, const LinW& src, int heads, int d, int dpad, Half2Ptr dst, int row_offset) {
+static void pack_heads(Ctx& c, const LinW& src, int heads, int d, int dpad, Half2Ptr dst, int row_offset,
+                       const float* in_scale = nullptr) {
   for (int h = 0; h < heads; ++h)
-    pack_linear_launch(mptr(c, src.wi), src.in, d, dst, row_offset + h * dpad, c.stream, src.out, h * d);
+    pack_linear_launch(mptr(c, src.wi), src.in, d, dst, row_offset + h * dpad, c.stream, src.out, h * d, in_scale);
 }
 
 static void pack_resblock(Ctx& c, ResBlockW& r, int passes) {
@@ -93,21 +95,45 @@ static void pack_st(Ctx& c, SpatialTransformerW& s, int passes) {
   pack_norm(c, s.norm), pack_norm(c, s.ln1), pack_norm(c, s.ln2), pack_norm(c, s.ln3);
   pack_conv(c, s.proj_in), pack_conv(c, s.proj_out);
   const int hd = s.heads * s.dpad;
+  // The three LayerNorms of the TransformerBlock (unet/mod.rs:523-525) have no launch: gamma is folded into the weights of the
+  // GEMM that consumes the normalised tensor (W' = diag(gamma) W), u = column sums of the packed W' (the exact fp16 values the
+  // tensor cores multiply), v = beta^T W (+ bias); the GEMM reads the raw tensor and applies rstd * (acc - mean * u) + v.
+  // The v vectors come from a scratch packing with beta in place of gamma (hi + lo = 22 bits of beta * W).
+  Half2Ptr scratch = alloc_half2(c.work, (size_t)8 * s.c * s.c);
+  auto fold = [&](WeightOp& w, float*& u_hi, float*& u_full, float*& v, const std::function<void(Half2Ptr, const float*)>& pack,
+                  const NormW& ln) {
+    pack(w.p, ln.gamma);
+    u_hi = c.packed.get<float>(w.N), u_full = c.packed.get<float>(w.N), v = c.packed.get<float>(w.N);
+    rowsum_f16_launch(w.p, w.N, w.K, u_hi, u_full, c.stream);
+    SDB_CUDA(cudaMemsetAsync(scratch.hi, 0, (size_t)w.N * w.K * 2, c.stream));  // head-pad rows stay zero
+    SDB_CUDA(cudaMemsetAsync(scratch.lo, 0, (size_t)w.N * w.K * 2, c.stream));
+    pack(scratch, ln.beta);
+    rowsum_f16_launch(scratch, w.N, w.K, nullptr, v, c.stream);
+  };
   s.w_qkv1.p = alloc_half2(c.packed, (size_t)3 * hd * s.c), s.w_qkv1.N = 3 * hd, s.w_qkv1.K = s.c;
-  pack_heads(c, s.attn1.query, s.heads, s.d, s.dpad, s.w_qkv1.p, 0);
-  pack_heads(c, s.attn1.key, s.heads, s.d, s.dpad, s.w_qkv1.p, hd);
-  pack_heads(c, s.attn1.value, s.heads, s.d, s.dpad, s.w_qkv1.p, 2 * hd);
+  fold(s.w_qkv1, s.u_qkv_hi, s.u_qkv_full, s.v_qkv, [&](Half2Ptr dst, const float* sc) {
+    pack_heads(c, s.attn1.query, s.heads, s.d, s.dpad, dst, 0, sc);
+    pack_heads(c, s.attn1.key, s.heads, s.d, s.dpad, dst, hd, sc);
+    pack_heads(c, s.attn1.value, s.heads, s.d, s.dpad, dst, 2 * hd, sc);
+  }, s.ln1);
   pack_lin(c, s.attn1.out), s.w_o1 = s.attn1.out.packed;
   s.w_q2.p = alloc_half2(c.packed, (size_t)hd * s.c), s.w_q2.N = hd, s.w_q2.K = s.c;
-  pack_heads(c, s.attn2.query, s.heads, s.d, s.dpad, s.w_q2.p, 0);
+  fold(s.w_q2, s.u_q2_hi, s.u_q2_full, s.v_q2,
+       [&](Half2Ptr dst, const float* sc) { pack_heads(c, s.attn2.query, s.heads, s.d, s.dpad, dst, 0, sc); }, s.ln2);
   s.w_kv2.p = alloc_half2(c.packed, (size_t)2 * hd * 768), s.w_kv2.N = 2 * hd, s.w_kv2.K = 768;
   pack_heads(c, s.attn2.key, s.heads, s.d, s.dpad, s.w_kv2.p, 0);
   pack_heads(c, s.attn2.value, s.heads, s.d, s.dpad, s.w_kv2.p, hd);
   pack_lin(c, s.attn2.out), s.w_o2 = s.attn2.out.packed;
   s.w_geglu.p = alloc_half2(c.packed, (size_t)8 * s.c * s.c), s.w_geglu.N = 8 * s.c, s.w_geglu.K = s.c;
   s.geglu_bias = c.packed.get<float>((size_t)8 * s.c);
-  pack_geglu_launch(mptr(c, s.geglu.wi), mptr(c, s.geglu.bi), s.c, 4 * s.c, 64, s.w_geglu.p, s.geglu_bias, c.stream);
+  fold(s.w_geglu, s.u_geglu_hi, s.u_geglu_full, s.v_geglu, [&](Half2Ptr dst, const float* sc) {
+    pack_geglu_launch(mptr(c, s.geglu.wi), mptr(c, s.geglu.bi), s.c, 4 * s.c, 64, dst, dst.hi == s.w_geglu.p.hi ? s.geglu_bias : nullptr,
+                      c.stream, sc);
+  }, s.ln3);
+  add_vec_launch(s.v_geglu, s.geglu_bias, 8 * s.c, s.v_geglu, c.stream);  // v = beta^T W + b (packed order)
   pack_lin(c, s.ff);
+  SDB_CUDA(cudaStreamSynchronize(c.stream));  // the scratch packing lives in the work arena
+  c.work.reset();
 }
 static void pack_resnet(Ctx& c, ResnetW& r, int passes) {
   r.passes = passes;
@@ -417,6 +443,9 @@ struct CtxState {
 };
 
 // reference unet/mod.rs:461-481 + 521-527 + 641-653 + 551-592
+// The block's residual stream y lives as an fp16 hi + lo pair (22 significant bits; no fp32 copy): every GEMM that reads it as
+// an operand takes the pair as it is, every GEMM that adds to it reads and rewrites the pair in place. The three LayerNorms have
+// no launch (see pack_st): the producers of y leave row statistics, the consumers normalise in their epilogue.
 static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxState& cs, const CtxKV& kv, const Act& x,
                                     Act& out) {
   Ctx& c = f.c;
@@ -426,28 +455,30 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   const int HW = x.H * x.W;
   const long long Mt = (long long)f.nb * HW;
   const int C = s.c, hd = s.heads * s.dpad;
+  const int ls = ln_slots(C);
   // GroupNorm (no activation) -> proj_in (1x1 conv == GEMM over tokens)
   ActOp a = f.gn_operand(x, nullptr, s.norm, false, lo);
-  float* y = c.work.get<float>((size_t)Mt * C);
+  Half2Ptr y16 = f.half2((size_t)Mt * C, true);
+  float* st1 = c.work.get<float>((size_t)Mt * ls * 2);
+  float* st2 = c.work.get<float>((size_t)Mt * ls * 2);
+  float* st3 = c.work.get<float>((size_t)Mt * ls * 2);
   {
     Epilogue ep;
-    ep.out_f32 = y, ep.bias = s.proj_in.bias;
+    ep.out_f16 = y16, ep.bias = s.proj_in.bias, ep.ln_out = st1;
     run_gemm(c, G_CONV1, a, nullptr, s.proj_in.packed, P, ep);
   }
-  Half2Ptr l16 = f.half2((size_t)Mt * C, lo);
   Half2Ptr o16 = f.half2((size_t)Mt * C, lo);
-  auto ln = [&](const NormW& nw) {
-    KernelScope ks(c, KC_LAYERNORM, 0, (double)Mt * C * 6.0);
-    layernorm_launch(y, (int)Mt, C, nw.gamma, nw.beta, nw.eps, l16, nullptr, c.stream);
+  auto ln_consume = [&](Epilogue& ep, const float* stats, const NormW& nw, const float* u_hi, const float* u_full, const float* v) {
+    ep.ln_in = stats, ep.ln_in_slots = ls, ep.ln_C = C, ep.ln_eps = nw.eps, ep.ln_u_hi = u_hi, ep.ln_u_full = u_full, ep.bias = v;
   };
-  // ---- self attention: x += out(attn(q,k,v = LN1(x)))
-  ln(s.ln1);
-  // one GEMM for q | k | v (head-padded columns); the attention kernel takes V as it is written here (MN-major operand)
+  // ---- self attention: x += out(attn(q,k,v = LN1(x))); one GEMM for q | k | v (head-padded columns), the attention kernel
+  // takes V as it is written here (MN-major operand)
   __half* qkv = c.work.get<__half>((size_t)Mt * 3 * hd);
   {
     Epilogue ep;
     ep.out_f16.hi = qkv;
-    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_qkv1, P, ep);
+    ln_consume(ep, st1, s.ln1, s.u_qkv_hi, s.u_qkv_full, s.v_qkv);
+    run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.w_qkv1, P, ep);
   }
   {
     AttnOp at;
@@ -460,16 +491,16 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   }
   {
     Epilogue ep;
-    ep.out_f32 = y, ep.residual = y, ep.bias = s.attn1.out.bias;
+    ep.out_f16 = y16, ep.residual16 = y16, ep.bias = s.attn1.out.bias, ep.ln_out = st2;
     run_gemm(c, G_LINEAR, f.rows_operand(o16, Mt, C), nullptr, s.w_o1, P, ep);
   }
   // ---- cross attention: x += out(attn(q = LN2(x), k,v = context))
-  ln(s.ln2);
   __half* q2 = c.work.get<__half>((size_t)Mt * hd);
   {
     Epilogue ep;
     ep.out_f16.hi = q2;
-    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_q2, P, ep);
+    ln_consume(ep, st2, s.ln2, s.u_q2_hi, s.u_q2_full, s.v_q2);
+    run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.w_q2, P, ep);
   }
   {
     AttnOp at;
@@ -483,22 +514,21 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   }
   {
     Epilogue ep;
-    ep.out_f32 = y, ep.residual = y, ep.bias = s.attn2.out.bias;
+    ep.out_f16 = y16, ep.residual16 = y16, ep.bias = s.attn2.out.bias, ep.ln_out = st3;
     run_gemm(c, G_LINEAR, f.rows_operand(o16, Mt, C), nullptr, s.w_o2, P, ep);
   }
-  // ---- GEGLU MLP: x += lin(x_a * gelu(gate))
-  ln(s.ln3);
+  // ---- GEGLU MLP: x += lin(x_a * gelu(gate)), LN3 folded into the GEGLU projection
   const int Pm = c.opt_mlp_passes ? c.opt_mlp_passes : P;  // pass policy of the MLP pair (DESIGN.md "precision")
   Half2Ptr g16 = f.half2((size_t)Mt * 4 * C, Pm >= 2 || c.opt_precision >= 2);
   {
     Epilogue ep;
-    ep.geglu = 1, ep.bias = s.geglu_bias, ep.out_f16 = g16;
-    run_gemm(c, G_LINEAR, f.rows_operand(l16, Mt, C), nullptr, s.w_geglu, Pm, ep);
+    ep.geglu = 1, ep.out_f16 = g16;
+    ln_consume(ep, st3, s.ln3, s.u_geglu_hi, s.u_geglu_full, s.v_geglu);
+    run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.w_geglu, Pm, ep);
   }
-  Half2Ptr y16 = f.half2((size_t)Mt * C, lo);
   {
     Epilogue ep;
-    ep.out_f32 = y, ep.residual = y, ep.bias = s.ff.bias, ep.out_f16 = y16;
+    ep.out_f16 = y16, ep.residual16 = y16, ep.bias = s.ff.bias;
     run_gemm(c, G_LINEAR, f.rows_operand(g16, Mt, 4 * C), nullptr, s.ff.packed, Pm, ep);
   }
   // ---- proj_out + residual with the block input

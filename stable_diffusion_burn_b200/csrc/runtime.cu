@@ -81,6 +81,8 @@ KernelScope::KernelScope(Ctx& c_, int cls_, double flops, double bytes, double i
   c.cls_flops[cls] += flops;
   c.cls_bytes[cls] += bytes;
   c.cls_issued[cls] += issued;
+  static FILE* label_log = getenv("SDB_LABEL_LOG") ? fopen(getenv("SDB_LABEL_LOG"), "w") : nullptr;  // launch-order labels (ncu join)
+  if (label_log) fprintf(label_log, "%s\t%s\n", kernel_class_name(cls), c.dbg_label.c_str()), fflush(label_log);
   if (on) {
     ev.cls = cls;
     ev.flops = flops;
@@ -197,7 +199,7 @@ void run_attention(Ctx& c, const AttnOp& a) {
   const CUtensorMap mv = a.v_mn ? make_mat_map(a.vT, a.ldv, (long long)a.nb * a.k_rows, 128)
                                 : make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
   const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
-  if (c.debug_sync || c.profiling) {
+  if (c.debug_sync || c.profiling || getenv("SDB_LABEL_LOG")) {
     char buf[200];
     snprintf(buf, sizeof(buf), "attention nb=%d heads=%d d=%d dpad=%d Nq=%d Nk=%d ldq=%d ldk=%d ldv=%d kvlen=%p", a.nb, a.heads,
              a.d, a.dpad, a.Nq, a.Nk, a.ldq, a.ldk, a.ldv, (const void*)a.kvlen);
@@ -346,11 +348,12 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
     split = (iters + per - 1) / per;
   }
   p.split_k = split;
-  static const bool gemm_dbg = getenv("SDB_GEMM_DBG") != nullptr;
+  static const bool gemm_dbg = getenv("SDB_GEMM_DBG") != nullptr || getenv("SDB_LABEL_LOG") != nullptr;
   if (c.debug_sync || c.profiling || gemm_dbg) {
     char buf[256];
-    snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d BN=%d split=%d passes=%d geglu=%d tile=%dx%dx%d cluster=%d",
-             kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, BN, split, passes, ep.geglu, p.TN, p.TH, p.TW, p.cluster);
+    snprintf(buf, sizeof(buf), "gemm kind=%d n=%d H=%d W=%d P=%d C0=%d C1=%d N=%d K=%d xk=%d BN=%d split=%d passes=%d geglu=%d epi=%s%s tile=%dx%dx%d cluster=%d",
+             kind, a0.n, a0.H, a0.W, a0.P, a0.C, a1in ? a1.C : 0, w.N, w.K, p.xkc * 64, BN, split, passes, ep.geglu,
+             ep.gn ? "gn" : (ep.ln_out ? "lns" : (ep.ln_in ? "lnc" : "-")), ep.residual16.hi ? "+r16" : (ep.residual ? "+r32" : ""), p.TN, p.TH, p.TW, p.cluster);
     c.dbg_label = buf;
   }
 
@@ -380,6 +383,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
   p.ln_in = ep.ln_in, p.ln_in_slots = ep.ln_in_slots, p.ln_C = ep.ln_C, p.ln_eps = ep.ln_eps;
   p.ln_u = passes >= 3 ? ep.ln_u_full : ep.ln_u_hi;
   SDB_CHECK(!ep.ln_in || (p.ln_u && ep.ln_in_slots > 0 && ep.ln_C == w.K && kind == G_LINEAR), "LayerNorm-consuming GEMM: arguments");
+  SDB_CHECK(!ep.ln_in || (!ep.residual && !ep.rowbias && !ep.residual16.hi), "LayerNorm-consuming GEMM: no residual / row bias");
   SDB_CHECK(!ep.ln_out || kind == G_LINEAR, "LayerNorm statistics: rows must be tokens");
   p.res_hi = ep.residual16.hi, p.res_lo = ep.residual16.lo;
   SDB_CHECK(!ep.residual16.hi || (ep.residual16.lo && !ep.residual && !ep.rowbias), "fp16-pair residual: needs both halves, excludes the fp32 residual / row bias");

@@ -174,3 +174,35 @@ def test_gemm_extra_k(ctx, M, K, XK, N, passes):
     e = rel(out, ref)
     print(f"extra-K M={M} K={K}+{XK} N={N} passes={passes}: rel L2 {e:.3e}")
     assert e < 3e-5
+
+
+# ------------------------------------------------------------------ LayerNorm folded into the GEMMs around it
+@pytest.mark.parametrize("M,K0,C,N,passes,geglu,second", [
+    (300, 320, 320, 1152, 3, False, False), (2048, 640, 640, 1920, 3, False, True), (512, 1280, 1280, 1280, 1, False, True),
+    (130, 320, 320, 2560, 3, True, True), (1024, 640, 640, 5120, 1, True, False), (64, 1280, 1280, 384, 3, False, False)])
+def test_layernorm_folded_into_gemms(ctx, M, K0, C, N, passes, geglu, second):
+    """y from a producing GEMM (row statistics in its epilogue, fp16 hi/lo residual pair updated in place), LayerNorm applied by
+    the consuming GEMM as rstd * (acc - mean * u) + v: against fp64 LayerNorm + matmul (+ GEGLU)."""
+    rng = np.random.default_rng(M + N)
+    a = rng.standard_normal((M, K0)).astype(np.float32)
+    a2 = rng.standard_normal((M, K0)).astype(np.float32) if second else None
+    w0 = (rng.standard_normal((K0, C)) / math.sqrt(K0)).astype(np.float32)
+    b0 = (rng.standard_normal(C) * 0.5 + 1.5).astype(np.float32)  # rows with a mean well away from zero: the cancellation case
+    g = (1 + 0.1 * rng.standard_normal(C)).astype(np.float32); be = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    w1 = (rng.standard_normal((C, N)) / math.sqrt(C)).astype(np.float32)
+    b1 = rng.standard_normal(N).astype(np.float32) * 0.3
+    y = a.astype(np.float64) @ w0.astype(np.float64) + b0
+    if second:
+        y = y + a2.astype(np.float64) @ w0.astype(np.float64) + b0
+    mu = y.mean(-1, keepdims=True); var = ((y - mu) ** 2).mean(-1, keepdims=True)
+    ln = (y - mu) / np.sqrt(var + 1e-5) * g + be
+    if passes == 1:  # single-pass consumers see the fp16-rounded raw y and fp16-rounded folded weights: bound, not equality
+        tol = 1.5e-3
+    else:
+        tol = 4e-5
+    pre = ln @ w1.astype(np.float64) + b1
+    ref = pre[:, :N // 2] * _gelu_erf(pre[:, N // 2:]) if geglu else pre
+    out = ctx.test_ln_fold(a, w0, b0, g, be, w1, b1, a2=a2, passes=passes, geglu=geglu)
+    e = rel(out, ref)
+    print(f"LN folded M={M} C={C} N={N} passes={passes} geglu={geglu} two producers={second}: rel L2 {e:.3e}")
+    assert e < tol
