@@ -158,7 +158,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int main_iters = p.num_taps * p.kc;
   const int total_iters = main_iters + p.xkc;
   const int per_split = (total_iters + p.split_k - 1) / p.split_k;
-  const int it_begin = blockIdx.z * per_split;
+  // grid.z is the K split — or, for the folded nearest-2x upsample conv (p.up2, never split), the output phase (a, b): the four
+  // 2x2-tap phase convolutions of one layer run as ONE launch; phase shifts the taps, the weight rows and the output pixel
+  const int up_a = p.up2 ? (int)(blockIdx.z >> 1) : 0, up_b = p.up2 ? (int)(blockIdx.z & 1) : 0;
+  const int kz = p.up2 ? 0 : (int)blockIdx.z;
+  const int b_row0 = col0 + (p.up2 ? (int)blockIdx.z * p.N : 0);  // first weight row of this tile (phase-major packing)
+  const int it_begin = kz * per_split;
   const int it_end = min(total_iters, it_begin + per_split);
 
   const uint32_t crank = TWO ? cluster_ctarank() : 0;
@@ -209,13 +214,13 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int bk = (it < main_iters ? it : it - main_iters) * BK;
         uint8_t* sb = smem + s * L::BYTES + L::A_TILES * A_TILE_BYTES;
         if (!TWO) {
-          tma_load_2d(sb, &bm[0], &full_bar[s], bk, col0);
-          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &bm[1], &full_bar[s], bk, col0);
+          tma_load_2d(sb, &bm[0], &full_bar[s], bk, b_row0);
+          if (PASSES >= 3) tma_load_2d(sb + L::B_TILE_BYTES, &bm[1], &full_bar[s], bk, b_row0);
         } else {
           // rows [crank*BN/2, +BN/2) of the weight tile into this CTA's smem, bytes reported to the leader's barrier
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
-          tma_load_2d_2sm(sb, &bm[0], fb, bk, col0 + crank * (BN / 2));
-          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &bm[1], fb, bk, col0 + crank * (BN / 2));
+          tma_load_2d_2sm(sb, &bm[0], fb, bk, b_row0 + crank * (BN / 2));
+          if (PASSES >= 3) tma_load_2d_2sm(sb + L::B_TILE_BYTES, &bm[1], fb, bk, b_row0 + crank * (BN / 2));
         }
       };
       auto load_a = [&](int it, int s) {
@@ -225,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           const int cc = it - tap * p.kc;
           src = cc >= p.kc0 ? 1 : 0;
           c0 = (cc - (src ? p.kc0 : 0)) * BK;
-          cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cp = p.tap_ph[tap];
+          cw = w0 + p.tap_dw[tap] + up_b, ch = h0 + p.tap_dh[tap] + up_a, cp = p.tap_ph[tap];
         } else {
           const int e = it - main_iters;
           src = e >= p.xkc0 ? 3 : 2;
@@ -252,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         for (int it = it_begin + npre; it < it_end; ++it) {
           const CUtensorMap* bm = it < main_iters ? maps.b : maps.bx;
           const int bk = (it < main_iters ? it : it - main_iters) * BK;
-          const int row = col0 + (TWO ? crank * (BN / 2) : 0);
+          const int row = b_row0 + (TWO ? crank * (BN / 2) : 0);
           tma_prefetch_l2_2d(&bm[0], bk, row);
           if (PASSES >= 3) tma_prefetch_l2_2d(&bm[1], bk, row);
         }
@@ -335,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int pn = n0 + r / (p.TW * p.TH);
     const int row_ok = ((pw < p.W) && (phh < p.H) && (pn < p.nimg)) ? 1 : 0;
     // output row index (< 2^31 rows); -1 marks a row outside the tensor
-    const int m = row_ok ? ((pn * p.OH + phh * p.os + p.oa) * p.OW + pw * p.os + p.ob) : -1;
+    const int m = row_ok ? ((pn * p.OH + phh * p.os + p.oa + up_a) * p.OW + pw * p.os + p.ob + up_b) : -1;
 
     // ---- work that needs no accumulator, done while the main loop runs: the element offsets of the 8 rows this lane
     // serves in every column chunk (rr = 4 i + sub), the bias of each chunk, and the first chunk's addends (residual or
@@ -454,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     if (p.split_k > 1) {
       // raw partial sums -> workspace [split][M][N]
       const size_t Mtot = (size_t)p.nimg * p.OH * p.OW;
-      float* wsbase = p.ws + (size_t)blockIdx.z * Mtot * p.N;
+      float* wsbase = p.ws + (size_t)kz * Mtot * p.N;
 #pragma unroll 1
       for (int c = half * 32; c < BN; c += CSTEP) {
         uint32_t v[32];
@@ -488,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       {
         const int rows_per = (BM + p.split_k - 1) / p.split_k;
-        const int r0 = blockIdx.z * rows_per, r1 = min(BM, r0 + rows_per);
+        const int r0 = kz * rows_per, r1 = min(BM, r0 + rows_per);
         constexpr int C4 = BN / 4;
         // thread -> (row lane, fixed 4-column group): a thread's GroupNorm column sums stay in registers across its rows
         constexpr int RL = (EW * 32) / C4;  // row lanes
@@ -556,7 +561,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           // fold the row lanes in a fixed order, then the channel buckets: this CTA's partial for its slice of the tile rows
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
           const int nbk_tile = BN / p.gn_bucket, nbk_total = p.N / p.gn_bucket;
-          const int slot = p.gn_slot0 + gnt.tile * p.split_k + blockIdx.z;
+          const int slot = p.gn_slot0 + gnt.tile * p.split_k + kz;
           const float* red = reinterpret_cast<const float*>(gn_red);
           for (int it = te; it < gnt.tn * nbk_tile; it += EW * 32) {
             const int k = it / nbk_tile, b = it - k * nbk_tile;
@@ -725,7 +730,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       if constexpr (kGN) {
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");  // every quarter's column sums are in shared memory
-        gn_write_partials(p, gn_cs, BN, threadIdx.x - 64, EW * 32, gnt, col0, 0);
+        gn_write_partials(p, gn_cs, BN, threadIdx.x - 64, EW * 32, gnt, col0, p.up2 ? (int)blockIdx.z * p.gn_phase_slots : 0);
       }
     }
     tc_fence_before();
@@ -772,7 +777,7 @@ static void launch_epi(const GemmMaps& maps, const GemmParams& p, cudaStream_t s
   static DeviceOnce once;
   if (once.first())
     SDB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, STAGES, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.split_k);
+  dim3 grid(p.tiles_n * p.tiles_h * p.tiles_w, (p.N + BN - 1) / BN, p.up2 ? 4 : p.split_k);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid, cfg.blockDim = dim3(64 + 32 * EW), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -806,7 +811,7 @@ bool gemm_tc_supports(int BN, int epi) {
 
 template <int BN, int PASSES, int CG>
 static void launch_cg(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
-  const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * p.split_k;
+  const long long ctas = (long long)p.tiles_n * p.tiles_h * p.tiles_w * ((p.N + BN - 1) / BN) * (p.up2 ? 4 : p.split_k);
   constexpr int SH = pick_stages_half<BN, PASSES, CG>();
   constexpr bool half_ok = SH * StageLayout<BN, PASSES, CG>::BYTES <= 104 * 1024 && SH * StageLayout<BN, PASSES, CG>::BYTES >= 8 * 32 * 144 * 2;
   // many short tiles: two co-resident CTAs per SM overlap one tile's epilogue with the other's mainloop

@@ -27,6 +27,8 @@ struct GemmParams {
   int xkc, xkc0;       // extra-K chunks appended after the taps (total, and those from source 2)
   int8_t tap_dh[9], tap_dw[9], tap_ph[9];
   int split_k;
+  int up2, gn_phase_slots; // up2 = 1: folded nearest-2x upsample conv, grid.z = the 4 output phases (weights packed [4][N][K], taps
+                           // / output pixel shifted by the phase); gn_phase_slots = GroupNorm partial slots one phase writes
   int cluster;             // 1, or 2 = CTA pairs along M issue tcgen05.mma.cta_group::2 (256 x BN)
   // epilogue
   float* out_f32;          // [M][ldc] or null

@@ -34,6 +34,9 @@ struct GnSrc {
 // folds groups of 64 partial slots: out [n][gn_fold_slots(slots)][nbk][2]
 int gn_fold_slots(int slots);
 void gn_fold_launch(const float* part, int cap, int slots, int nbk, int n, float* out, cudaStream_t st);
+// group sums [n][32][2] of one tensor from its producer-side partials (cap / slots as in GnSrc)
+void gn_sums_from_partials_launch(const float* part, int cap, int slots, int nbk, int C, int bucket, int n, double* sums,
+                                  cudaStream_t st);
 void gn_apply_launch(const GnSrc& s0, const GnSrc& s1, int bucket, int n, int H, int W, int silu, const float* gamma,
                      const float* beta, float eps, Half2Ptr out, cudaStream_t st);
 // mode bits

@@ -287,15 +287,32 @@ struct Fwd {
     gn_tickets = c.work.get<unsigned int>((size_t)slots * nb * 2);  // one ticket counter per (slot, image); the second half is spare
     SDB_CUDA(cudaMemsetAsync(gn_tickets, 0, sizeof(unsigned int) * slots * nb * 2, c.stream));
   }
-  // GroupNorm statistics of cat(x0,x1): returns the [nb][32][2] sums
-  double* stats(const float* x0, int C0, const float* x1, int C1, int HW) {
+  // GroupNorm statistics of one tensor as [nb][32][2] sums (for the fused GroupNorm + SiLU + small-Cout convs): from the
+  // producer's partials when it left any, else by reading the tensor
+  double* stats(const Act& x) {
     SDB_CHECK(gn_slot < gn_slots, "GroupNorm statistics slots exhausted");
     double* sums = gn_sums + (size_t)gn_slot * nb * 64;
     unsigned int* tk = gn_tickets + (size_t)gn_slot * nb * 2;
     gn_slot++;
+    const int HW = x.H * x.W;
+    if (x.gn.slots > 0) {
+      const int nbk = x.C / x.gn.bucket;
+      const float* part = x.gn.buf;
+      int cap = x.gn.cap, slots = x.gn.slots;
+      if (slots > 128) {
+        const int s2 = gn_fold_slots(slots);
+        float* folded = c.work.get<float>((size_t)nb * s2 * nbk * 2);
+        KernelScope ks(c, KC_GN_STATS, 0, (double)nb * slots * nbk * 8.0);
+        gn_fold_launch(part, cap, slots, nbk, nb, folded, c.stream);
+        part = folded, cap = s2, slots = s2;
+      }
+      KernelScope ks(c, KC_GN_STATS, 0, (double)nb * slots * nbk * 8.0);
+      gn_sums_from_partials_launch(part, cap, slots, nbk, x.C, x.gn.bucket, nb, sums, c.stream);
+      return sums;
+    }
     float* part = c.work.get<float>(gn_stats_partial_floats(nb, HW));
-    KernelScope ks(c, KC_GN_STATS, 0, (double)nb * HW * (C0 + C1) * 4.0);
-    gn_stats_launch(x0, C0, x1, C1, nb, HW, sums, part, tk, c.stream);
+    KernelScope ks(c, KC_GN_STATS, 0, (double)nb * HW * x.C * 4.0);
+    gn_stats_launch(x.p, x.C, nullptr, 0, nb, HW, sums, part, tk, c.stream);
     return sums;
   }
   Act act16(int H, int W, int C) {
@@ -682,7 +699,7 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   }
   // out: GroupNorm + SiLU + conv 320 -> 4 (:138-140), fused, fp32 on CUDA cores, NCHW result
   {
-    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
+    double* sums = f.stats(x);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 320 * 4);
     conv3x3_small_cout_launch(x.p, f.nb, H, W, 320, sums, m.norm_out.gamma, m.norm_out.beta, m.norm_out.eps, m.conv_out.w_small,
                               m.conv_out.bias, 4, io.out, c.stream);
@@ -806,7 +823,7 @@ static void vae_decode(Fwd& f, const float* d_latent, int H, int W, float pre_sc
   }
   // norm_out + SiLU + conv_out 128 -> 3 (autoencoder/mod.rs:215-216)
   {
-    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
+    double* sums = f.stats(x);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 128 * 3);
     conv3x3_small_cout_launch(x.p, f.nb, H, W, 128, sums, m.vae_norm_out.gamma, m.vae_norm_out.beta, m.vae_norm_out.eps,
                               m.vae_conv_out.w_small, m.vae_conv_out.bias, 3, d_img, c.stream);
@@ -860,7 +877,7 @@ static void vae_encode(Fwd& f, const float* d_img4, int H, int W, float* d_laten
   // norm_out + SiLU + conv_out 512 -> 8 (fp32 CUDA cores, NCHW), then quant_conv 8 -> 8 and the slice [0,4)
   float* y8 = c.work.get<float>((size_t)f.nb * 8 * H * W);
   {
-    double* sums = f.stats(x.p, x.C, nullptr, 0, H * W);
+    double* sums = f.stats(x);
     KernelScope ks(c, KC_SMALLCONV, 2.0 * f.nb * H * W * 9.0 * 512 * 8);
     conv3x3_small_cout_launch(x.p, f.nb, H, W, 512, sums, e.norm_out.gamma, e.norm_out.beta, e.norm_out.eps, e.conv_out.w_small,
                               e.conv_out.bias, 8, y8, c.stream);

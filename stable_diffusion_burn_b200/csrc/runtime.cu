@@ -440,10 +440,12 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
                          (ep.residual ? Mtot * nout * 4.0 : 0.0);
   const double bytes = a_bytes + w_bytes + o_bytes;  // per launch (a folded-upsample phase reads all of A and writes a quarter of the output)
 
-  for (int phase = 0; phase < phases_out; ++phase) {
-    const __half* whi = w.p.hi + (size_t)phase * w.N * w.K;
-    const __half* wlo = w.p.lo ? w.p.lo + (size_t)phase * w.N * w.K : nullptr;
-    const int wrows = w.rows ? w.rows : w.N;
+  {
+    // the folded-upsample conv runs its four output phases in ONE launch (grid.z = phase): weights are packed phase-major
+    // [4][N][K], so one map over 4 N rows serves them all
+    const __half* whi = w.p.hi;
+    const __half* wlo = w.p.lo;
+    const int wrows = (w.rows ? w.rows : w.N) * phases_out;
     const int bbox = pair ? BN / 2 : BN;
     maps.b[0] = make_w_map(whi, w.K, wrows, bbox, w.ld);
     maps.b[1] = maps.b[0];
@@ -454,16 +456,13 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       maps.bx[0] = make_w_map(xk->w.p.hi, xk->w.K, xrows, bbox, xk->w.ld);
       maps.bx[1] = passes >= 3 ? make_w_map(xk->w.p.lo, xk->w.K, xrows, bbox, xk->w.ld) : maps.bx[0];
     }
-    p.gn_slot0 = phase * (m_tiles / p.tiles_n) * split;
+    p.gn_slot0 = 0;
+    p.up2 = 0, p.gn_phase_slots = (m_tiles / p.tiles_n) * split;
     if (kind == G_CONV3_UP2) {
-      const int a = phase >> 1, b = phase & 1;
-      p.oa = a, p.ob = b;
-      for (int t = 0; t < 4; ++t) {
-        const int ti = t >> 1, tj = t & 1;
-        p.tap_dh[t] = (a == 0) ? (ti == 0 ? -1 : 0) : (ti == 0 ? 0 : 1);
-        p.tap_dw[t] = (b == 0) ? (tj == 0 ? -1 : 0) : (tj == 0 ? 0 : 1);
-        p.tap_ph[t] = 0;
-      }
+      // output phase (a, b) in {0,1}^2 sees the 2x2 window of source pixels at rows {h-1+a, h+a}, columns {w-1+b, w+b}: the
+      // kernel adds (a, b) = (blockIdx.z >> 1, blockIdx.z & 1) to the phase-0 taps and to the output pixel
+      p.up2 = 1, p.oa = 0, p.ob = 0;
+      for (int t = 0; t < 4; ++t) p.tap_dh[t] = (t >> 1) - 1, p.tap_dw[t] = (t & 1) - 1, p.tap_ph[t] = 0;
     }
     if (split > 1) {
       const size_t need = (size_t)split * (size_t)Mtot * w.N * sizeof(float);
@@ -484,7 +483,7 @@ void run_gemm(Ctx& c, int kind, const ActOp& a0in, const ActOp* a1in, const Weig
       }
       const std::string label = c.dbg_label;
       {
-        KernelScope ks(c, KC_GEMM, flops, bytes, flops * passes);
+        KernelScope ks(c, KC_GEMM, flops * phases_out, bytes * phases_out, flops * passes * phases_out);
         gemm_tc_launch(maps, p, BN, passes, c.stream);
       }
       if (dbg_on) {  // bring-up aid: cycle stamps of CTA (0,0,0), printed relative to kernel entry
