@@ -74,22 +74,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def window(self, t0, t1):
+        """clocks / throttle reasons of the samples taken in [t0, t1] (one nvidia-smi process serves every timed region of the
+        run: forking a second one from a process that holds a CUDA context, pinned buffers and NCCL threads hung rank 0)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for (t, r) in list(self.rows) if t0 <= t <= t1 + 0.25]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
 
 
 def host_threads():
@@ -309,15 +315,17 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup):
-        step_dev()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # one sampler process for the whole run, started before any timed region
+    for _ in range(args.warmup):
+        step_dev()
     l0 = ctx.launch_count()
+    w0 = time.time()
     ms = timed(step_dev, args.steps)
+    w1 = time.time()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.window(w0, w1) if rank == 0 else None
     value = world * n * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C ABI
@@ -339,11 +347,9 @@ def main():
         for _ in range(2):
             c5_dev()
         k5 = max(2, min(args.steps, 5))
-        s5 = ClockSampler(local)
-        if rank == 0:
-            s5.start()
+        w0 = time.time()
         ms5 = timed(c5_dev, k5)
-        clk5 = s5.stop() if rank == 0 else None
+        clk5 = sampler.window(w0, time.time()) if rank == 0 else None
         c5_e2e()
         ms5e = timed(c5_e2e, k5)
         c5 = {"workload": f"BASELINE configs[4]: SDv1-4 txt2img {args.size}x{args.size}, {args.ddim_steps} steps, cfg=7.5, "
@@ -383,6 +389,7 @@ def main():
                "sample": f"{what}; {step_s[0]:.2f} s/step x {args.ddim_steps} + decode {dec:.2f} s = {cpu_img_s:.1f} s/image"}
 
     if rank == 0:
+        sampler.stop()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

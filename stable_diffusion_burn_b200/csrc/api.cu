@@ -414,6 +414,8 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_splitk_min_iters = value;
   else if (k == "splitk_chunk")
     c.opt_splitk_chunk = value < 1 ? 1 : value;
+  else if (k == "attn_split")
+    c.opt_attn_split = value;
   else if (k == "prefetch_w")
     c.opt_prefetch_w = value;
   else if (k == "mlp_passes")
@@ -422,6 +424,8 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_gn_epilogue = value;
   else if (k == "skip_merge")
     c.opt_skip_merge = value;
+  else if (k == "gn_apply_ctas")
+    g_gn_apply_ctas = value < 1 ? 1 : value;
   else if (k == "gn_min_pix")
     g_gn_min_pix = value < 1 ? 1 : value;
   else

@@ -21,11 +21,18 @@ namespace sdb {
 // VMN = false: V arrives transposed, V^T [d][keys] (K-major B operand of P.V: two boxes of [DPAD rows][64 keys]).
 // VMN = true : V arrives as the projection wrote it, V [keys][d] (MN-major B operand: DC boxes of [128 keys][64 channels]) —
 //              no transposing GEMM in front of the kernel.
-template <int DPAD, int NG, bool VMN = false>
+// QK3 = true : q and k arrive as fp16 hi + lo pairs and S = q_hi k_hi^T + q_lo k_hi^T + q_hi k_lo^T (the 3-term split product of
+//              the GEMMs): the logits are fp32-class. With single fp16 operands a logit of magnitude ~30 (peaked softmax of a
+//              trained checkpoint) carries an absolute error ~1e-2, i.e. ~1 % on the dominant probabilities — the largest
+//              single error source of a UNet step on realistic-statistics weights (tests/test_realstats_gpu.py).
+template <int DPAD, int NG, bool VMN = false, bool QK3 = false>
 struct AttnCfg {
   static constexpr int DC = (DPAD + 63) / 64;                          // 64-wide chunks of the head dim
-  static constexpr int Q_TILE = DC * 128 * 128;                         // [128 rows][64] x DC, 128 B rows
-  static constexpr int K_BYTES = DC * 128 * 128;
+  static constexpr int QK_PARTS = QK3 ? 2 : 1;                          // hi (+ lo) copies of the Q and K tiles
+  static constexpr int Q_HALF = DC * 128 * 128;                         // [128 rows][64] x DC, 128 B rows
+  static constexpr int Q_TILE = QK_PARTS * Q_HALF;
+  static constexpr int K_HALF = DC * 128 * 128;
+  static constexpr int K_BYTES = QK_PARTS * K_HALF;
   static constexpr int V_CHUNK = VMN ? 128 * 128 : ((DPAD * 128 + 1023) / 1024) * 1024;   // VMN: [128 keys][64 ch]; else [DPAD rows][64 keys]
   static constexpr int V_BYTES = (VMN ? DC : 2) * V_CHUNK;
   static constexpr int V_TX = VMN ? DC * 128 * 128 : 2 * DPAD * 128;    // bytes one V stage receives
@@ -45,11 +52,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int DPAD, int NG, bool VMN>
+template <int DPAD, int NG, bool VMN, bool QK3>
 __global__ void __launch_bounds__(64 + 128 * NG, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
-                 const __grid_constant__ CUtensorMap mv, const AttnParams p) {
-  using Cfg = AttnCfg<DPAD, NG, VMN>;
+                 const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mq_lo,
+                 const __grid_constant__ CUtensorMap mk_lo, const AttnParams p) {
+  using Cfg = AttnCfg<DPAD, NG, VMN, QK3>;
   constexpr int DC = Cfg::DC, ST = Cfg::ST;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,18 +125,26 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 #pragma unroll
       for (int g = 0; g < NG; ++g)
 #pragma unroll
-        for (int c = 0; c < DC; ++c)
+        for (int c = 0; c < DC; ++c) {
           tma_load_2d(sQ + g * Cfg::Q_TILE + c * 16384, &mq, q_full, p.q_col0 + h * DPAD + c * 64,
                       s * p.q_rows_per_sample + q0 + g * 128);
+          if (QK3)
+            tma_load_2d(sQ + g * Cfg::Q_TILE + Cfg::Q_HALF + c * 16384, &mq_lo, q_full, p.q_col0 + h * DPAD + c * 64,
+                        s * p.q_rows_per_sample + q0 + g * 128);
+        }
       for (int j = 0; j < T; ++j) {
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::K_BYTES);
 #pragma unroll
-        for (int c = 0; c < DC; ++c)
+        for (int c = 0; c < DC; ++c) {
           tma_load_2d(sK + st * Cfg::K_BYTES + c * 16384, &mk, &k_full[st], p.k_col0 + h * DPAD + c * 64,
                       s * p.k_rows_per_sample + j * 128);
+          if (QK3)
+            tma_load_2d(sK + st * Cfg::K_BYTES + Cfg::K_HALF + c * 16384, &mk_lo, &k_full[st], p.k_col0 + h * DPAD + c * 64,
+                        s * p.k_rows_per_sample + j * 128);
+        }
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], Cfg::V_TX);
         if (VMN) {
@@ -159,6 +175,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         for (int kk = 0; kk < DPAD / 16; ++kk) {
           const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
           umma_f16(tmem_base + g * 128, make_sdesc_sw128(qa + off), make_sdesc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+          if (QK3) {  // + q_lo k_hi^T + q_hi k_lo^T
+            umma_f16(tmem_base + g * 128, make_sdesc_sw128(qa + Cfg::Q_HALF + off), make_sdesc_sw128(ka + off), idesc_s, 1u);
+            umma_f16(tmem_base + g * 128, make_sdesc_sw128(qa + off), make_sdesc_sw128(ka + Cfg::K_HALF + off), idesc_s, 1u);
+          }
         }
         if (g == NG - 1) umma_commit(&k_empty[st]);  // the K stage is free once the last group's QK retires
         umma_commit(&s_full[g]);
@@ -318,40 +338,49 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   }
 }
 
-template <int DPAD, int NG, bool VMN>
-static void launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
-                         cudaStream_t st) {
-  constexpr int smem = AttnCfg<DPAD, NG, VMN>::SMEM;
+template <int DPAD, int NG, bool VMN, bool QK3>
+static void launch_attn2(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
+  constexpr int smem = AttnCfg<DPAD, NG, VMN, QK3>::SMEM;
   static DeviceOnce once;
   if (once.first())
-    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG, VMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG, VMN, QK3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
-  launch_k(attention_kernel<DPAD, NG, VMN>, grid, dim3(64 + 128 * NG), (size_t)smem, st, mq, mk, mv, p);
+  launch_k(attention_kernel<DPAD, NG, VMN, QK3>, grid, dim3(64 + 128 * NG), (size_t)smem, st, m.q, m.k, m.v, m.q_lo, m.k_lo, p);
 }
 template <int DPAD, int NG>
-static void launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
-                        cudaStream_t st) {
+static void launch_attn(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
   if (p.v_mn)
-    launch_attn2<DPAD, NG, true>(mq, mk, mv, p, st);
+    launch_attn2<DPAD, NG, true, false>(m, p, st);
   else
-    launch_attn2<DPAD, NG, false>(mq, mk, mv, p, st);
+    launch_attn2<DPAD, NG, false, false>(m, p, st);
 }
 
-void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
-                      cudaStream_t st) {
+bool attention_supports_qk3(int dpad) { return dpad == 48 || dpad == 80; }
+
+void attention_launch(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
   const bool two = p.Nq > 128;  // two ping-pong query tiles per CTA when there are at least two tiles of rows
+  if (p.qk3) {
+    // split q / k operands (levels 0-1 of the UNet: V always MN-major there). Shared memory: d = 40 keeps two query tiles and two
+    // K/V stages (225.5 KB); d = 80 fits one query tile and one stage
+    SDB_CHECK(p.v_mn && attention_supports_qk3(p.dpad), "split q/k attention: head dim / V layout");
+    if (p.dpad == 48)
+      two ? launch_attn2<48, 2, true, true>(m, p, st) : launch_attn2<48, 1, true, true>(m, p, st);
+    else
+      launch_attn2<80, 1, true, true>(m, p, st);
+    return;
+  }
   switch (p.dpad) {
     case 48:
-      two ? launch_attn<48, 2>(mq, mk, mv, p, st) : launch_attn<48, 1>(mq, mk, mv, p, st);
+      two ? launch_attn<48, 2>(m, p, st) : launch_attn<48, 1>(m, p, st);
       break;
     case 64:
-      launch_attn<64, 1>(mq, mk, mv, p, st);
+      launch_attn<64, 1>(m, p, st);
       break;
     case 80:
-      two ? launch_attn<80, 2>(mq, mk, mv, p, st) : launch_attn<80, 1>(mq, mk, mv, p, st);
+      two ? launch_attn<80, 2>(m, p, st) : launch_attn<80, 1>(m, p, st);
       break;
     case 160:
-      launch_attn<160, 1>(mq, mk, mv, p, st);
+      launch_attn<160, 1>(m, p, st);
       break;
     default:
       throw Error("attention: unsupported head dim " + std::to_string(p.dpad));

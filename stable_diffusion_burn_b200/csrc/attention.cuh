@@ -10,6 +10,7 @@ struct AttnParams {
   int q_rows_per_sample;      // row stride between samples in the Q matrix (and in the output)
   int k_rows_per_sample;      // row stride between samples in K (= column stride in V^T)
   int q_col0, k_col0;         // first column of head 0 inside the Q / K matrices
+  int qk3;                    // 1: q and k are fp16 hi + lo pairs, S is the 3-term split product (fp32-class logits)
   int v_mn, v_col0;           // v_mn = 1: V is a [keys][ldv] matrix (head h at columns v_col0 + h*dpad) consumed MN-major;
                               // v_mn = 0: V^T [heads*d][ldv] (sample s at columns s*k_rows)
   const int* kvlen;           // [nb] valid keys per sample, or null (= Nk)
@@ -20,7 +21,10 @@ struct AttnParams {
   int ldo;
 };
 
-void attention_launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& p,
-                      cudaStream_t st);
+struct AttnMaps {
+  CUtensorMap q, k, v, q_lo, k_lo;  // q_lo / k_lo: the lo halves (same geometry) when p.qk3, else copies of q / k
+};
+void attention_launch(const AttnMaps& m, const AttnParams& p, cudaStream_t st);
+bool attention_supports_qk3(int dpad);
 
 }  // namespace sdb

@@ -494,14 +494,16 @@ void gn_sums_from_partials_launch(const float* part, int cap, int slots, int nbk
   SDB_CUDA(cudaGetLastError());
 }
 
+int g_gn_apply_ctas = 592;  // measured (tools/step_time.py, ms per image): 1184 ?, 592 146.1, 296 149.3, 148 155.5
 void gn_apply_launch(const GnSrc& s0, const GnSrc& s1, int bucket, int n, int H, int W, int silu, const float* gamma,
                      const float* beta, float eps, Half2Ptr out, cudaStream_t st) {
   const int C = s0.C + s1.C, HW = H * W;
   SDB_CHECK(C % 64 == 0 && s0.C % 8 == 0 && C <= 2560 && bucket > 0 && s0.C % bucket == 0 && s1.C % bucket == 0 &&
                 (C / 32) % bucket == 0 && C / bucket <= 256,
             "GroupNorm apply: channel / bucket geometry");
-  // no co-residency constraint any more: ~4 CTAs per SM, at least one pixel each
-  int pix = (int)((((long long)HW * n) + 591) / 592);
+  // no co-residency constraint any more; every CTA repeats the fold of its image's partials (8-24 KB from L2), so the grid is
+  // kept to g_gn_apply_ctas CTAs (4 per SM by default), at least one pixel each
+  int pix = (int)((((long long)HW * n) + g_gn_apply_ctas - 1) / g_gn_apply_ctas);
   if (pix < 1) pix = 1;
   dim3 grid(ceil_div(HW, pix), n);
   launch_k(gn_apply_kernel, grid, dim3(256), (size_t)2 * C * sizeof(float), st, s0, s1, bucket, H, W, pix, silu, gamma, beta, eps,

@@ -450,7 +450,8 @@ static void run_resblock(Fwd& f, const NormW& n1, const ConvW& c1, const NormW& 
 
 // per-layer K / V^T of the context tokens (constant over the DDIM steps)
 struct CtxKV {
-  __half* kv = nullptr;  // [nb*Lpad][2*heads*dpad]: K | V of the context tokens, head-padded
+  __half* kv = nullptr;     // [nb*Lpad][2*heads*dpad]: K | V of the context tokens, head-padded
+  __half* kv_lo = nullptr;  // lo halves (the split QK^T of the 3-pass levels reads K as a hi + lo pair)
 };
 struct CtxState {
   Half2Ptr ctx16;  // [nb*Lpad][768]
@@ -490,10 +491,13 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   };
   // ---- self attention: x += out(attn(q,k,v = LN1(x))); one GEMM for q | k | v (head-padded columns), the attention kernel
   // takes V as it is written here (MN-major operand)
+  // on the 3-pass levels q and k also get their lo halves: the attention kernel forms the logits as a 3-term split product
+  const bool qk_split = lo && c.opt_attn_split && attention_supports_qk3(s.dpad);
   __half* qkv = c.work.get<__half>((size_t)Mt * 3 * hd);
+  __half* qkv_lo = qk_split ? c.work.get<__half>((size_t)Mt * 3 * hd) : nullptr;
   {
     Epilogue ep;
-    ep.out_f16.hi = qkv;
+    ep.out_f16.hi = qkv, ep.out_f16.lo = qkv_lo;
     ln_consume(ep, st1, s.ln1, s.u_qkv_hi, s.u_qkv_full, s.v_qkv);
     run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.w_qkv1, P, ep);
   }
@@ -502,6 +506,7 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
     at.q = qkv, at.ldq = 3 * hd, at.q_col0 = 0, at.q_rows = HW;
     at.k = qkv, at.ldk = 3 * hd, at.k_col0 = hd, at.k_rows = HW;
     at.vT = qkv, at.ldv = 3 * hd, at.v_mn = 1, at.v_col0 = 2 * hd;
+    at.q_lo = qkv_lo, at.k_lo = qkv_lo;
     at.nb = f.nb, at.heads = s.heads, at.d = s.d, at.dpad = s.dpad, at.Nq = HW, at.Nk = HW;
     at.out = o16, at.ldo = C;
     run_attention(c, at);
@@ -513,9 +518,10 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
   }
   // ---- cross attention: x += out(attn(q = LN2(x), k,v = context))
   __half* q2 = c.work.get<__half>((size_t)Mt * hd);
+  __half* q2_lo = qk_split ? c.work.get<__half>((size_t)Mt * hd) : nullptr;
   {
     Epilogue ep;
-    ep.out_f16.hi = q2;
+    ep.out_f16.hi = q2, ep.out_f16.lo = q2_lo;
     ln_consume(ep, st2, s.ln2, s.u_q2_hi, s.u_q2_full, s.v_q2);
     run_gemm(c, G_LINEAR, f.rows_operand(y16, Mt, C), nullptr, s.w_q2, P, ep);
   }
@@ -524,6 +530,7 @@ static void run_spatial_transformer(Fwd& f, SpatialTransformerW& s, const CtxSta
     at.q = q2, at.ldq = hd, at.q_col0 = 0, at.q_rows = HW;
     at.k = kv.kv, at.ldk = 2 * hd, at.k_col0 = 0, at.k_rows = cs.Lpad;
     at.vT = kv.kv, at.ldv = 2 * hd, at.v_mn = 1, at.v_col0 = hd;
+    at.q_lo = q2_lo, at.k_lo = kv.kv_lo;
     at.nb = f.nb, at.heads = s.heads, at.d = s.d, at.dpad = s.dpad, at.Nq = HW, at.Nk = cs.Lpad;
     at.kvlen = cs.kvlen;
     at.out = o16, at.ldo = C;
@@ -576,9 +583,10 @@ static void prepare_context(Fwd& f, const float* d_ctx /*[nb][Lpad][768] zero pa
     const int hd = s.heads * s.dpad;
     CtxKV& kv = cs.kv[i];
     kv.kv = c.work.get<__half>((size_t)rows * 2 * hd);
+    kv.kv_lo = c.work.get<__half>((size_t)rows * 2 * hd);
     {
       Epilogue ep;
-      ep.out_f16.hi = kv.kv;
+      ep.out_f16.hi = kv.kv, ep.out_f16.lo = kv.kv_lo;
       run_gemm(c, G_LINEAR, f.rows_operand(cs.ctx16, rows, 768), nullptr, s.w_kv2, 3, ep);
     }
   }
@@ -1309,20 +1317,29 @@ void model_test_attention(Ctx& c, const float* q, const float* k, const float* v
   const int d = C / heads, dpad = (d % 16 == 0) ? d : (d + 15) / 16 * 16, hd = heads * dpad;
   const int Nkp = round_up(Nk, 8);
   std::vector<__half> hq((size_t)n * Nq * hd, __float2half(0.f)), hkv((size_t)n * Nkp * 2 * hd, __float2half(0.f));
+  std::vector<__half> hq_lo(hq.size(), __float2half(0.f)), hkv_lo(hkv.size(), __float2half(0.f));
+  auto split = [](float v, __half& hi, __half& lo) {
+    hi = __float2half(v);
+    lo = __float2half(v - __half2float(hi));
+  };
   for (int s = 0; s < n; ++s)
     for (int i = 0; i < Nq; ++i)
       for (int h = 0; h < heads; ++h)
         for (int j = 0; j < d; ++j)
-          hq[((size_t)s * Nq + i) * hd + h * dpad + j] = __float2half(q[((size_t)s * Nq + i) * C + h * d + j]);
+          split(q[((size_t)s * Nq + i) * C + h * d + j], hq[((size_t)s * Nq + i) * hd + h * dpad + j], hq_lo[((size_t)s * Nq + i) * hd + h * dpad + j]);
   for (int s = 0; s < n; ++s)
     for (int i = 0; i < Nk; ++i)
       for (int h = 0; h < heads; ++h)
         for (int j = 0; j < d; ++j) {
-          hkv[((size_t)s * Nkp + i) * 2 * hd + h * dpad + j] = __float2half(k[((size_t)s * Nk + i) * C + h * d + j]);
+          split(k[((size_t)s * Nk + i) * C + h * d + j], hkv[((size_t)s * Nkp + i) * 2 * hd + h * dpad + j], hkv_lo[((size_t)s * Nkp + i) * 2 * hd + h * dpad + j]);
           hkv[((size_t)s * Nkp + i) * 2 * hd + hd + h * dpad + j] = __float2half(v[((size_t)s * Nk + i) * C + h * d + j]);
         }
   __half* dq = c.work.get<__half>(hq.size());
   __half* dkv = c.work.get<__half>(hkv.size());
+  __half* dq_lo = c.work.get<__half>(hq.size());
+  __half* dkv_lo = c.work.get<__half>(hkv.size());
+  SDB_CUDA(cudaMemcpyAsync(dq_lo, hq_lo.data(), hq.size() * 2, cudaMemcpyHostToDevice, c.stream));
+  SDB_CUDA(cudaMemcpyAsync(dkv_lo, hkv_lo.data(), hkv.size() * 2, cudaMemcpyHostToDevice, c.stream));
   Half2Ptr o16;
   o16.hi = c.work.get<__half>((size_t)n * Nq * C);
   o16.lo = c.work.get<__half>((size_t)n * Nq * C);
@@ -1335,6 +1352,7 @@ void model_test_attention(Ctx& c, const float* q, const float* k, const float* v
   at.q = dq, at.ldq = hd, at.q_rows = Nq;
   at.k = dkv, at.ldk = 2 * hd, at.k_rows = Nkp;
   at.vT = dkv, at.ldv = 2 * hd, at.v_mn = 1, at.v_col0 = hd;
+  at.q_lo = dq_lo, at.k_lo = dkv_lo;  // used by the head dims that have the split-product kernel (40, 80) unless attn_split = 0
   at.nb = n, at.heads = heads, at.d = d, at.dpad = dpad, at.Nq = Nq, at.Nk = Nkp;
   at.kvlen = dlen;
   at.out = o16, at.ldo = C;

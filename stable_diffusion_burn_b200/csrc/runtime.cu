@@ -194,11 +194,15 @@ void run_attention(Ctx& c, const AttnOp& a) {
   p.causal = a.causal;
   p.scale = (float)(1.0 / std::sqrt((double)a.d));
   p.out_hi = a.out.hi, p.out_lo = a.out.lo, p.ldo = a.ldo;
-  const CUtensorMap mq = make_mat_map(a.q, a.ldq, (long long)a.nb * a.q_rows, 128);
-  const CUtensorMap mk = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
-  const CUtensorMap mv = a.v_mn ? make_mat_map(a.vT, a.ldv, (long long)a.nb * a.k_rows, 128)
-                                : make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
-  const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;
+  AttnMaps am;
+  am.q = make_mat_map(a.q, a.ldq, (long long)a.nb * a.q_rows, 128);
+  am.k = make_mat_map(a.k, a.ldk, (long long)a.nb * a.k_rows, 128);
+  am.v = a.v_mn ? make_mat_map(a.vT, a.ldv, (long long)a.nb * a.k_rows, 128)
+                : make_mat_map(a.vT, a.ldv, (long long)a.heads * a.d, a.dpad);
+  p.qk3 = (a.q_lo && a.k_lo && a.v_mn && attention_supports_qk3(a.dpad) && c.opt_attn_split) ? 1 : 0;
+  am.q_lo = p.qk3 ? make_mat_map(a.q_lo, a.ldq, (long long)a.nb * a.q_rows, 128) : am.q;
+  am.k_lo = p.qk3 ? make_mat_map(a.k_lo, a.ldk, (long long)a.nb * a.k_rows, 128) : am.k;
+  const double flops = 4.0 * a.nb * a.heads * (double)a.Nq * a.Nk * a.d;  // algorithmic (the split QK^T issues 2x this)
   if (c.debug_sync || c.profiling || getenv("SDB_LABEL_LOG")) {
     char buf[200];
     snprintf(buf, sizeof(buf), "attention nb=%d heads=%d d=%d dpad=%d Nq=%d Nk=%d ldq=%d ldk=%d ldv=%d kvlen=%p", a.nb, a.heads,
@@ -206,7 +210,7 @@ void run_attention(Ctx& c, const AttnOp& a) {
     c.dbg_label = buf;
   }
   KernelScope ks(c, KC_ATTN, flops, 0);
-  attention_launch(mq, mk, mv, p, c.stream);
+  attention_launch(am, p, c.stream);
 }
 
 static int pow2_floor(int x) {

@@ -130,6 +130,7 @@ struct Ctx {
   int opt_skip_merge = 1; // ResBlock skip 1x1 conv folded into conv_out's K loop (needs raw16)
   int opt_raw16 = 1;      // epilogues also write the fp16 hi/lo copy a later raw-operand consumer needs (no staging launch)
   int opt_mlp_passes = 0;   // 0: the transformer MLP (GEGLU + ff) follows its level's pass policy; 1: single fp16 pass everywhere
+  int opt_attn_split = 1;   // fused attention on the 3-pass levels takes q / k as fp16 hi + lo pairs (fp32-class logits)
   int opt_prefetch_w = 1;   // weight-bound GEMMs (<= 4 M tiles) prefetch their weight strip into L2 ahead of griddepcontrol.wait
   int opt_gn_epilogue = 1;  // GroupNorm statistics produced by the GEMM epilogue that writes the tensor (no stats pass, no rendezvous)
   int opt_cluster = 1;    // CTA pairs issue cta_group::2 MMAs (256 x BN) wherever the M-tile count is even and K is not split
@@ -191,6 +192,8 @@ struct AttnOp {
   int ldq = 0, q_col0 = 0, q_rows = 0;
   const __half* k = nullptr;
   int ldk = 0, k_col0 = 0, k_rows = 0;
+  const __half* q_lo = nullptr;  // lo halves of q / k (same layout): both set -> the 3-term split QK^T (head dims 40 / 80)
+  const __half* k_lo = nullptr;
   const __half* vT = nullptr;  // V^T [heads*d][ldv], or with v_mn = 1 the row-major V [nb*k_rows][ldv] (head-padded like k)
   int ldv = 0;
   int v_mn = 0, v_col0 = 0;

@@ -106,6 +106,41 @@ def make_params(seed: int = 0, which=None) -> dict:
     return out
 
 
+def realistic_stats(params: dict, seed: int = 7) -> dict:
+    """Reshapes the i.i.d. synthetic weights towards the statistics of a trained SD-v1 checkpoint (none exists offline): per
+    output channel gains drawn log-normal (sigma 0.5: a few channels 3-5x the rest, i.e. outlier activations), GroupNorm /
+    LayerNorm gamma in [0.4, 1.6] and beta in +-0.4, sharper attention logits (query / key weights x 1.7), larger biases.
+    A pure function of (name, channel, seed) — the GPU test applies the same transform before sdb_set_tensor."""
+    out = {}
+    for name, a in params.items():
+        a = np.asarray(a, np.float32)
+        leaf = name.rsplit("/", 1)[-1]
+        parent = name.rsplit("/", 1)[0]
+        if name == "alpha_cumulative_products" or "embedding" in name:
+            out[name] = a
+            continue
+        is_norm = any(k in parent.rsplit("/", 1)[-1] for k in ("norm", "_ln", "layer_norm"))
+        if is_norm:
+            u = uniform01(name + "#r", a.size, seed).reshape(a.shape)
+            out[name] = (0.4 + 1.2 * u).astype(np.float32) if leaf == "weight" else ((u * 2 - 1) * np.float32(0.4)).astype(np.float32)
+            continue
+        if leaf == "weight" and a.ndim in (2, 4):
+            n_out = a.shape[1] if a.ndim == 2 else a.shape[0]  # Linear [in,out], conv OIHW
+            u1 = uniform01(parent + "#g1", n_out, seed).astype(np.float64)
+            u2 = uniform01(parent + "#g2", n_out, seed).astype(np.float64)
+            z = np.sqrt(-2.0 * np.log(np.maximum(u1, 1e-7))) * np.cos(2 * np.pi * u2)  # Box-Muller
+            g = np.exp(0.5 * z)
+            g = (g / np.sqrt(np.mean(g * g))).astype(np.float32)  # unit RMS gain: the layer's output scale is kept
+            if parent.endswith(("/query", "/key")):
+                g = g * np.float32(1.7)
+            out[name] = (a * (g[None, :] if a.ndim == 2 else g[:, None, None, None])).astype(np.float32)
+        elif leaf == "bias":
+            out[name] = (a * np.float32(3.0)).astype(np.float32)
+        else:
+            out[name] = a
+    return out
+
+
 # ---------------------------------------------------------------- inputs ----
 def make_latent(n: int, h: int, w: int, seed: int = 1234) -> np.ndarray:
     """N(0,1) init latent [n,4,h,w]; image i uses stream seed+i."""

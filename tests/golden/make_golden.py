@@ -204,5 +204,25 @@ def finish(P, t0):
     print("done", time.time() - t0)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and ONLY != {"realstats"}:
     main()
+
+
+def realstats_golden():
+    """UNet outputs on the REALISTIC-STATISTICS weights (synth.realistic_stats: log-normal channel gains, wide norm affine,
+    sharper attention logits): `python tests/golden/make_golden.py realstats`."""
+    from stable_diffusion_burn_b200 import topology
+    P = O.Params(synth.realistic_stats(synth.make_params(0, topology.unet_params())))
+    keep = {}
+    with torch.no_grad():
+        y = O.unet_forward(P, torch.from_numpy(synth.make_latent(2, 32, 32, seed=7)), 321, torch.from_numpy(synth.make_context(2, 13, seed=5)))
+        keep["b2_32"] = y.numpy()
+        y = O.unet_forward(P, torch.from_numpy(synth.make_latent(1, 64, 64)), 999, torch.from_numpy(synth.make_context(1, 77)))
+        keep["n1_64_L77"] = y.numpy()
+    np.savez_compressed(os.path.join(OUT, "unet_realstats.npz"), **keep)
+    print("realstats", {k: float(np.sqrt((v ** 2).mean())) for k, v in keep.items()})
+
+
+if __name__ == "__main__" and ONLY == {"realstats"}:
+    torch.set_num_threads(os.cpu_count())
+    realstats_golden()

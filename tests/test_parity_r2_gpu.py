@@ -206,3 +206,23 @@ def test_layernorm_folded_into_gemms(ctx, M, K0, C, N, passes, geglu, second):
     e = rel(out, ref)
     print(f"LN folded M={M} C={C} N={N} passes={passes} geglu={geglu} two producers={second}: rel L2 {e:.3e}")
     assert e < tol
+
+
+# ------------------------------------------------------------------ .mpk model file -> device weights (row f3)
+def test_mpk_file_feeds_the_weight_registry(ctx, tmp_path):
+    """A NamedMpk-style file holding the VAE decoder (written by mpk.save_mpk: format unverified against burn) replaces the
+    decoder weights of a context initialised with a DIFFERENT seed; the decode then matches the seed-0 fixture."""
+    from stable_diffusion_burn_b200 import mpk, topology
+    params = synth.make_params(0, which=topology.vae_decoder_params())
+    f = os.path.join(tmp_path, "decoder.mpk")
+    mpk.save_mpk(f, params)
+    try:
+        ctx.init_synthetic(1)
+        n = mpk.load_into(ctx, f)
+        assert n == len(params)  # every decoder tensor + the schedule
+        ctx.finalize_weights()
+        g = np.load(os.path.join(GOLD, "vae_16.npz"))
+        assert rel(ctx.decode_latent(synth.make_latent(1, 16, 16, seed=21)), g["img"]) < 1e-3
+    finally:
+        ctx.init_synthetic(0)
+        ctx.finalize_weights()
