@@ -12,10 +12,24 @@ semantics below are restated from their published definitions:
   activation::softmax  exp(x-max)/sum
   Tensor::repeat(&[..]) per-dimension tiling
 
-PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture for
-this path (its only test is the tokenizer KAT, src/tokenizer.rs:205-221) and it cannot be
-compiled or run here (no rustc/cargo, crates not vendored). This oracle is therefore
-anchored on the reference's call sites only; tests/golden/ holds outputs of THIS oracle.
+PARITY PINNED against the reference's own Python model. The reference holds no golden vector, known-answer test or fixture
+for this path (its only test is the tokenizer KAT, src/tokenizer.rs:205-221) and its Rust cannot be compiled here (no
+rustc/cargo, crates not vendored) — but it ships the author's tinygrad twin of the model, python/dump.py (the program that
+writes the dump-dir the Rust loaders read). tests/ref_shim/ runs that file UNMODIFIED on a minimal tinygrad stand-in
+(tinygrad is not installed), saves the model with the reference's own savers (python/save.py, unet.py, autoencoder.py, clip.py,
+stablediffusion.py), reads that tree back with this repo's dump-dir reader and compares forwards (tests/test_ref_pin_cpu.py):
+    UNetModel.__call__ (dump.py:326-350)      vs unet_forward      2.2e-6 rel L2 (this oracle's GELU switched to tinygrad's
+                                                                     tanh form for that comparison only; erf is the Rust form)
+    Decoder / post_quant_conv (:76-108,149-150)   vs decode_latent     1.2e-6
+    Encoder / quant_conv (:110-148)           vs encode_image      9.4e-7
+    AutoencoderKL.__call__ (:144-150)         vs decode(encode)    2.1e-6
+    CLIPTextTransformer.__call__ (:452-461)   vs clip_forward      8.3e-7
+    timestep_embedding (:273-277, test.py:31-35) vs timestep_embedding 2.6e-6
+and the tree the reference's saver writes equals, file for file (names, metadata, small tensors), the tree this repo's writer
+produces. tests/golden/ref_python.npz holds the reference model's outputs on the synthetic weights (script:
+tests/ref_shim/make_ref_golden.py); the other tests/golden/*.npz are outputs of THIS oracle (erf GELU), which the GPU suite is
+held to. What stays unpinned: the DDIM sampler / CFG arithmetic of src/model/stablediffusion/mod.rs:102-192 (no Python twin
+exists; restated from the Rust, section "pipeline" below) and burn's erf-GELU / LayerNorm definitions (third-party crates).
 
 `dtype` may be torch.float32 (the parity target) or torch.float64 (truth for tolerance
 budgeting). `emu` optionally rounds GEMM-class operands to a tensor-core input format to

@@ -37,6 +37,15 @@ extern "C" {
     fn sdb_sample_image(ctx: *mut SdbCtx, context: *const f32, n: c_int, l: c_int, uncond: *const f32, lu: c_int,
                         guidance_scale: f64, n_steps: c_int, init_latent: *const f32, seed: u64, h: c_int, w: c_int,
                         rgb: *mut u8) -> c_int;
+    fn sdb_sample_latent(ctx: *mut SdbCtx, context: *const f32, n: c_int, l: c_int, uncond: *const f32, lu: c_int,
+                         guidance_scale: f64, n_steps: c_int, init_latent: *const f32, seed: u64, h: c_int, w: c_int,
+                         latent_out: *mut f32) -> c_int;
+    fn sdb_latent_to_image(ctx: *mut SdbCtx, latent: *const f32, n: c_int, h: c_int, w: c_int, rgb: *mut u8) -> c_int;
+    fn sdb_forward_diffuser(ctx: *mut SdbCtx, latent: *const f32, timestep: i32, context: *const f32, n: c_int, l: c_int,
+                            uncond: *const f32, lu: c_int, guidance_scale: f64, h: c_int, w: c_int, pred: *mut f32,
+                            out_uncond: *mut f32, out_cond: *mut f32) -> c_int;
+    fn sdb_nccl_unique_id(id128: *mut c_void) -> c_int;
+    fn sdb_broadcast_weights(ctx: *mut SdbCtx, id128: *const c_void, rank: c_int, world: c_int) -> c_int;
     #[allow(dead_code)]
     fn sdb_sample_image_dev(ctx: *mut SdbCtx, d_context: *const c_void, n: c_int, l: c_int, d_uncond: *const c_void,
                             lu: c_int, guidance_scale: f64, n_steps: c_int, d_init_latent: *const c_void, h: c_int,
@@ -130,6 +139,58 @@ impl StableDiffusion {
                              init_latent.map_or(std::ptr::null(), |s| s.as_ptr()), seed, h as c_int, w as c_int, rgb.as_mut_ptr())
         })?;
         Ok(rgb.chunks(8 * h * 8 * w * 3).map(|c| c.to_vec()).collect())
+    }
+}
+
+impl StableDiffusion {
+    /// `StableDiffusion::sample_latent(context, unconditional_context, scale, n_steps) -> Tensor<B, 4>`
+    /// (src/model/stablediffusion/mod.rs:102-160); returns the final latent [n, 4, 64, 64].
+    #[allow(clippy::too_many_arguments)]
+    pub fn sample_latent(&self, context: &[f32], [n, l]: [usize; 2], unconditional_context: &[f32], lu: usize,
+                         unconditional_guidance_scale: f64, n_steps: usize, init_latent: Option<&[f32]>, seed: u64)
+                         -> Result<Vec<f32>, SdbError> {
+        let (h, w) = (64usize, 64usize);
+        let mut latent = vec![0f32; n * 4 * h * w];
+        self.check(unsafe {
+            sdb_sample_latent(self.ctx, context.as_ptr(), n as c_int, l as c_int, unconditional_context.as_ptr(), lu as c_int,
+                              unconditional_guidance_scale, n_steps as c_int,
+                              init_latent.map_or(std::ptr::null(), |s| s.as_ptr()), seed, h as c_int, w as c_int, latent.as_mut_ptr())
+        })?;
+        Ok(latent)
+    }
+
+    /// `StableDiffusion::latent_to_image(latent) -> Vec<Vec<u8>>` (src/model/stablediffusion/mod.rs:69-100).
+    pub fn latent_to_image(&self, latent: &[f32], [n, h, w]: [usize; 3]) -> Result<Vec<Vec<u8>>, SdbError> {
+        let mut rgb = vec![0u8; n * 8 * h * 8 * w * 3];
+        self.check(unsafe { sdb_latent_to_image(self.ctx, latent.as_ptr(), n as c_int, h as c_int, w as c_int, rgb.as_mut_ptr()) })?;
+        Ok(rgb.chunks(8 * h * 8 * w * 3).map(|c| c.to_vec()).collect())
+    }
+
+    /// `forward_diffuser(latent, timestep, context, unconditional_context, scale)` (src/model/stablediffusion/mod.rs:162-192):
+    /// the guided noise prediction of one step.
+    #[allow(clippy::too_many_arguments)]
+    pub fn forward_diffuser(&self, latent: &[f32], [n, h, w]: [usize; 3], timestep: i32, context: &[f32], l: usize,
+                            unconditional_context: &[f32], lu: usize, unconditional_guidance_scale: f64) -> Result<Vec<f32>, SdbError> {
+        let mut pred = vec![0f32; n * 4 * h * w];
+        self.check(unsafe {
+            sdb_forward_diffuser(self.ctx, latent.as_ptr(), timestep, context.as_ptr(), n as c_int, l as c_int,
+                                 unconditional_context.as_ptr(), lu as c_int, unconditional_guidance_scale, h as c_int, w as c_int,
+                                 pred.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut())
+        })?;
+        Ok(pred)
+    }
+
+    /// Multi-GPU init: rank 0 calls `nccl_unique_id()` and ships the 128 bytes to the other ranks by any means; every rank then
+    /// calls `broadcast_weights(&id, rank, world)` (one ncclBroadcast of the weight arena from rank 0) and `finalize_weights()`.
+    pub fn nccl_unique_id() -> Result<[u8; 128], SdbError> {
+        let mut id = [0u8; 128];
+        if unsafe { sdb_nccl_unique_id(id.as_mut_ptr() as *mut c_void) } != 0 {
+            return Err(SdbError("ncclGetUniqueId failed".into()));
+        }
+        Ok(id)
+    }
+    pub fn broadcast_weights(&self, id: &[u8; 128], rank: usize, world: usize) -> Result<(), SdbError> {
+        self.check(unsafe { sdb_broadcast_weights(self.ctx, id.as_ptr() as *const c_void, rank as c_int, world as c_int) })
     }
 }
 

@@ -321,6 +321,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+// fp32 -> fp16 "hi" half of an operand pair, SATURATING at the largest finite fp16 (65504) instead of rounding to infinity: the lo
+// half then carries the excess (x - 65504 is itself an fp16 value up to 65504), so a hi + lo pair represents |x| < 131008 with
+// ~2^-19 relative precision and nothing turns into inf / NaN on the multi-pass paths; a single-pass operand (hi only) clips.
+__device__ __forceinline__ __half2 f2h2_sat(float a, float b) {
+  return __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // erf GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. fp32-level) — 1 MUFU.EX2 + 1 MUFU.RCP + 7 FMA

@@ -42,7 +42,7 @@ __device__ __noinline__ void epilogue_store(float4 f, unsigned int o32, unsigned
   }
   if (out_f32) *reinterpret_cast<float4*>(out_f32 + o32) = f;
   if (out_f16) {
-    __half2 h[2] = {__floats2half2_rn(f.x, f.y), __floats2half2_rn(f.z, f.w)};
+    __half2 h[2] = {f2h2_sat(f.x, f.y), f2h2_sat(f.z, f.w)};
     *reinterpret_cast<uint2*>(out_f16 + o16) = *reinterpret_cast<uint2*>(h);
     if (out_f16_lo) {
       const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
@@ -109,9 +109,12 @@ __host__ __device__ constexpr int min_ctas_per_sm() {
 // the shared-memory carve-out at its maximum L1 holds nothing, so every spill access is an L2 round trip (ncu on the q|k|v
 // projection: 225 K local loads + 152 K local stores, 48 MB of local traffic for 19 MB of output, long-scoreboard the top stall).
 // 4 warps (192 threads per CTA) leave 170 registers per thread: no spills.
-template <int BN, int PASSES, int STAGES, int CG>
+// The GEGLU epilogue is the exception: it is bound by its own arithmetic (erf-GELU on every output), 16 warps per SM beat 8
+// even at 96 registers (measured on the level-0 GEGLU projection: 8 warps 74 us, 4 warps 90 us), and as a compile-time variant
+// (EPI_GEGLU*) it no longer carries the other epilogues' registers.
+template <int BN, int PASSES, int STAGES, int CG, int EPI>
 __host__ __device__ constexpr int epilogue_warps() {
-  return min_ctas_per_sm<BN, PASSES, STAGES, CG>() == 2 ? 4 : 8;
+  return (min_ctas_per_sm<BN, PASSES, STAGES, CG>() == 2 && EPI < 4) ? 4 : 8;
 }
 
 // EPI selects what the epilogue does beside bias / residual / stores. It is a compile-time choice because the once-per-CTA
@@ -121,15 +124,18 @@ __host__ __device__ constexpr int epilogue_warps() {
 //   EPI_LNC    the A operand is the RAW input of a LayerNorm whose gamma is folded into the weights: the normalisation is applied
 //              here as a rank-1 correction, out = rstd_r * (acc - mean_r * u_c) + v_c  (u = column sums of the folded weights,
 //              v = beta^T W + bias arrives as `bias`), from the row statistics the producer of A left (EPI_LNS)
-enum : int { EPI_PLAIN = 0, EPI_GN = 1, EPI_LNS = 2, EPI_LNC = 3 };
+//   EPI_GEGLU / EPI_GEGLU_LNC   x * gelu_erf(gate) on column-interleaved (x | gate) tiles (unet/mod.rs:578-592), without / with
+//              the LayerNorm-consuming correction
+enum : int { EPI_PLAIN = 0, EPI_GN = 1, EPI_LNS = 2, EPI_LNC = 3, EPI_GEGLU = 4, EPI_GEGLU_LNC = 5 };
 
 template <int BN, int PASSES, int STAGES, int CG, int EPI>
-__global__ void __launch_bounds__(64 + 32 * epilogue_warps<BN, PASSES, STAGES, CG>(), min_ctas_per_sm<BN, PASSES, STAGES, CG>())
+__global__ void __launch_bounds__(64 + 32 * epilogue_warps<BN, PASSES, STAGES, CG, EPI>(), min_ctas_per_sm<BN, PASSES, STAGES, CG>())
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  constexpr bool kGN = EPI == EPI_GN, kLNS = EPI == EPI_LNS, kLNC = EPI == EPI_LNC;
+  constexpr bool kGN = EPI == EPI_GN, kLNS = EPI == EPI_LNS, kLNC = EPI == EPI_LNC || EPI == EPI_GEGLU_LNC;
+  constexpr bool kGEGLU = EPI == EPI_GEGLU || EPI == EPI_GEGLU_LNC;
   using L = StageLayout<BN, PASSES, CG>;
   constexpr bool TWO = CG == 2;
-  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();  // epilogue warps
+  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG, EPI>();  // epilogue warps
   constexpr int EG = EW / 4;                                    // warps sharing one TMEM lane quarter
   constexpr int CSTEP = 32 * EG;                                // column stride between the chunks of one warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -353,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     float4 bvs[NCHUNK], ad[8];
     const float* ad_ptr = p.residual ? p.residual : p.rowbias;
     const bool res_pair = p.res_hi != nullptr;  // the residual lives as an fp16 hi + lo pair (row stride ldc16)
-    const bool plain = p.split_k == 1 && !p.geglu;
+    const bool plain = p.split_k == 1 && !kGEGLU;
     // EPI_LNC: mean / rstd of this lane's own accumulator row, from the partial row sums the producer of A left
     float ln_mu = 0.f, ln_rs = 0.f;
     float mu8[8], rs8[8];
@@ -456,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       epilogue_store(f, (unsigned)(mr * p.ldc + col), (unsigned)(mr * p.ldc16 + col), p.out_f32, p.out_f16, p.out_f16_lo, p.act);
     };
 
-    if (p.split_k > 1) {
+    if (!kGEGLU && p.split_k > 1) {
       // raw partial sums -> workspace [split][M][N]
       const size_t Mtot = (size_t)p.nimg * p.OH * p.OW;
       float* wsbase = p.ws + (size_t)kz * Mtot * p.N;
@@ -586,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           tk[1] = 0u;
         }
       }
-    } else if (p.geglu) {
+    } else if (kGEGLU) {
       // tile columns [0,BN/2) = x, [BN/2,BN) = gate; output columns blockIdx.y*BN/2 + [0,BN/2)
       constexpr int HB = BN / 2;
       const int ocol0 = blockIdx.y * HB;
@@ -770,7 +776,7 @@ constexpr int pick_stages_half() {
 template <int BN, int PASSES, int STAGES, int CG, int EPI>
 static void launch_epi(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   constexpr int smem = STAGES * StageLayout<BN, PASSES, CG>::BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
-  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG>();
+  constexpr int EW = epilogue_warps<BN, PASSES, STAGES, CG, EPI>();
   static_assert(STAGES * StageLayout<BN, PASSES, CG>::BYTES >= 2 * EW * 32 * 144, "epilogue staging tiles must fit in the stages");
   static_assert(4 * BN * 8 <= EW * 32 * 144 && ((EW * 32) / (BN / 4)) * 4 * (BN / 4) * 32 <= EW * 32 * 144,
                 "GroupNorm column sums must fit in the second staging bank");
@@ -793,6 +799,14 @@ static void launch_epi(const GemmMaps& maps, const GemmParams& p, cudaStream_t s
 template <int BN, int PASSES, int STAGES, int CG>
 static void launch_inst(const GemmMaps& maps, const GemmParams& p, cudaStream_t stream) {
   SDB_CHECK((p.gn_part != nullptr) + (p.ln_out != nullptr) + (p.ln_in != nullptr) <= 1, "one statistics role per launch");
+  if constexpr (BN == 128) {
+    if (p.geglu) {
+      SDB_CHECK(!p.gn_part && !p.ln_out && p.split_k == 1, "GEGLU epilogue: no statistics output, no split-K");
+      return p.ln_in ? launch_epi<BN, PASSES, STAGES, CG, EPI_GEGLU_LNC>(maps, p, stream)
+                     : launch_epi<BN, PASSES, STAGES, CG, EPI_GEGLU>(maps, p, stream);
+    }
+  }
+  SDB_CHECK(!p.geglu, "the GEGLU epilogue is built for 128-wide tiles");
   if constexpr (BN >= 128) {
     if (p.gn_part) return launch_epi<BN, PASSES, STAGES, CG, EPI_GN>(maps, p, stream);
   }

@@ -13,7 +13,7 @@ static inline int ceil_div(long long a, long long b) { return int((a + b - 1) / 
 __device__ __forceinline__ void split_store8(const float (&f)[8], __half* hi, __half* lo) {
   __half2 h[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) h[j] = f2h2_sat(f[2 * j], f[2 * j + 1]);
   *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h);
   if (lo) {
     __half2 l[4];
@@ -751,13 +751,16 @@ void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* 
 //   [4][pixel][4] so that the warp's float4 reads are conflict-free; the chunk's weights sit beside it (broadcast reads).
 // Each x element crosses HBM/L2 1.33 times (halo), against 9 times for the tap-by-tap warp-per-pixel kernel this replaces
 // (512 us -> ~70 us on the VAE's last conv).
-template <int COUT>
-__global__ void __launch_bounds__(256)
+// TH = rows of the CTA tile (threads = 32 * TH): 8 for large images; 2 for small ones, where an 8-row tile would leave most SMs
+// idle (UNet conv_out at 64x64, batch 2: 32 CTAs with TH = 8 -> 140 us). With so few warps per SM nothing hides the latency of a
+// chunk's loads, so the small variant takes 64 channels per round (5 rounds for 320 channels instead of 20).
+template <int COUT, int TH, int CK>
+__global__ void __launch_bounds__(32 * TH)
 conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, const double* __restrict__ sums,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                           const float* __restrict__ wp, const float* __restrict__ b, float* __restrict__ y) {
   pdl_enter();
-  constexpr int TH = 8, TW = 32, CK = 16, HP = TH + 2, WP = TW + 2, NPIX = HP * WP;
+  constexpr int TW = 32, HP = TH + 2, WP = TW + 2, NPIX = HP * WP;
   extern __shared__ float sm[];
   float* s_scale = sm;                           // [C]
   float* s_shift = sm + C;                       // [C]
@@ -779,7 +782,7 @@ conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, cons
     __syncthreads();  // the previous chunk's reads are done (and, first time round, the affine table is written)
     // halo tile: NPIX pixels x 4 channel quads
     for (int i = threadIdx.x; i < NPIX * (CK / 4); i += blockDim.x) {
-      const int pix = i >> 2, q = i & 3;
+      const int pix = i / (CK / 4), q = i % (CK / 4);
       const int hh = h0 - 1 + pix / WP, ww = w0 - 1 + pix % WP;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
@@ -819,16 +822,30 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
                                const float* beta, float eps, const float* w_packed, const float* b, int Cout,
                                float* y_nchw, cudaStream_t st) {
   SDB_CHECK(C % 16 == 0, "conv3x3_small_cout: channels must be a multiple of 16");
-  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), n);
-  auto smem = [&](int cout) { return (size_t)(2 * C + 4 * 10 * 34 * 4 + 9 * cout * 4 * 4) * sizeof(float); };
-  if (Cout == 4)
-    launch_k(conv3x3_small_cout_kernel<4>, grid, dim3(256), smem(4), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
-  else if (Cout == 3)
-    launch_k(conv3x3_small_cout_kernel<3>, grid, dim3(256), smem(3), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
-  else if (Cout == 8)
-    launch_k(conv3x3_small_cout_kernel<8>, grid, dim3(256), smem(8), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw);
-  else
+  // too few 8-row tiles to fill the machine -> 2-row tiles, 64 channels per round
+  const bool small = (long long)ceil_div(W, 32) * ceil_div(H, 8) * n < 2 * 148 && C % 64 == 0;
+  const int th = small ? 2 : 8, ck = small ? 64 : 16;
+  dim3 grid(ceil_div(W, 32), ceil_div(H, th), n), block(32 * th);
+  auto smem = [&](int cout) { return (size_t)(2 * C + ck * (th + 2) * 34 + 9 * cout * ck) * sizeof(float); };
+#define SDB_SMALL_CONV(CO)                                                                                                          \
+  if (small) {                                                                                                                      \
+    static DeviceOnce once;                                                                                                         \
+    if (once.first())                                                                                                               \
+      SDB_CUDA(cudaFuncSetAttribute(conv3x3_small_cout_kernel<CO, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    launch_k(conv3x3_small_cout_kernel<CO, 2, 64>, grid, block, smem(CO), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b,      \
+             y_nchw);                                                                                                               \
+  } else                                                                                                                            \
+    launch_k(conv3x3_small_cout_kernel<CO, 8, 16>, grid, block, smem(CO), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw)
+  if (Cout == 4) {
+    SDB_SMALL_CONV(4);
+  } else if (Cout == 3) {
+    SDB_SMALL_CONV(3);
+  } else if (Cout == 8) {
+    SDB_SMALL_CONV(8);
+  } else {
     throw Error("conv3x3_small_cout: Cout must be 3, 4 or 8");
+  }
+#undef SDB_SMALL_CONV
   SDB_CUDA(cudaGetLastError());
 }
 

@@ -3,7 +3,7 @@ unmodified on tests/ref_shim/tinygrad) on this repo's synthetic weights (seed 0)
 
   python tests/ref_shim/make_ref_golden.py
 
-How the synthetic weights get into the reference model: the reference's saver (python/stablediffusion.py:8-15) writes the
+How the synthetic weights get into the reference model: the reference's saver (python/stablediffusion.py:8-14) writes the
 randomly initialised model as a dump-dir; every file it wrote is matched back to the parameter it came from, which yields the
 dump-dir name (and orientation) of every parameter; the synthetic tensors are then assigned by that name.
 """

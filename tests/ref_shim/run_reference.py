@@ -59,7 +59,7 @@ def _fingerprint(a: np.ndarray):
 
 
 class Reference:
-    """The reference StableDiffusion object (python/dump.py:547-552) with random stand-in weights, plus the dump-dir name of
+    """The reference StableDiffusion object (python/dump.py:565-570) with random stand-in weights, plus the dump-dir name of
     every parameter, DERIVED by running the reference's own saver and matching what it wrote against the parameters."""
 
     def __init__(self, seed: int = 0, verbose: bool = False):
@@ -80,7 +80,7 @@ class Reference:
         self.model.alphas_cumprod.t = torch.from_numpy(np.asarray(alphas, np.float32).copy())
 
     def save(self, path: str):
-        """python/stablediffusion.py:8-15 save_stable_diffusion — the reference's writer of the tree the Rust side loads."""
+        """python/stablediffusion.py:8-14 save_stable_diffusion — the reference's writer of the tree the Rust side loads."""
         sink = io.StringIO()
         with contextlib.redirect_stdout(sys.stdout if self.verbose else sink):
             self.dump.sdsave.save_stable_diffusion(self.model, path)
@@ -134,19 +134,19 @@ class Reference:
 
     # ---- forwards (the reference's __call__ methods)
     def unet_forward(self, x, t, context):
-        """python/dump.py:327-350 UNetModel.__call__(x, timesteps, context); timesteps = Tensor([t]) as in :631."""
+        """python/dump.py:326-350 UNetModel.__call__(x, timesteps, context); timesteps = Tensor([t]) as in :631."""
         T = self.Tensor
         with torch.no_grad():
             return self.unet(T(np.asarray(x, np.float32)), T([float(t)]), T(np.asarray(context, np.float32))).numpy()
 
     def decode_latent(self, latent):
-        """python/dump.py:148-149: post_quant_conv then decoder (== Autoencoder::decode_latent, autoencoder/mod.rs:68-71)."""
+        """python/dump.py:149-150: post_quant_conv then decoder (== Autoencoder::decode_latent, autoencoder/mod.rs:68-71)."""
         T = self.Tensor
         with torch.no_grad():
             return self.vae.decoder(self.vae.post_quant_conv(T(np.asarray(latent, np.float32)))).numpy()
 
     def encode_image(self, img):
-        """python/dump.py:145-147: encoder, quant_conv, [:, 0:4] (== Autoencoder::encode_image, autoencoder/mod.rs:60-66)."""
+        """python/dump.py:145-148: encoder, quant_conv, [:, 0:4] (== Autoencoder::encode_image, autoencoder/mod.rs:60-66)."""
         T = self.Tensor
         with torch.no_grad():
             lat = self.vae.quant_conv(self.vae.encoder(T(np.asarray(img, np.float32))))
@@ -158,11 +158,11 @@ class Reference:
             return self.vae(self.Tensor(np.asarray(img, np.float32))).numpy()
 
     def clip_forward(self, tokens):
-        """python/dump.py:452-461 CLIPTextTransformer.__call__(input_ids[n, L])."""
+        """python/dump.py:449-454 CLIPTextTransformer.__call__(input_ids[n, L])."""
         with torch.no_grad():
             return self.clip(self.Tensor(torch.from_numpy(np.asarray(tokens, np.int64)))).numpy()
 
     def timestep_embedding(self, t):
-        """python/dump.py:273-277."""
+        """python/dump.py:274-278."""
         with torch.no_grad():
             return self.dump.timestep_embedding(self.Tensor([float(t)]), 320).numpy()

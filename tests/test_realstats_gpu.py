@@ -3,10 +3,13 @@
 No SD-v1.4 checkpoint exists offline; synth.realistic_stats reshapes the synthetic stream towards a trained checkpoint's
 statistics: log-normal per-channel gains (outlier channels 3-5x the rest, residual stream max ~65), GroupNorm / LayerNorm gamma
 in [0.4, 1.6], beta +-0.4, attention query / key weights x 1.7 (peaked softmax). Weights go in through sdb_set_tensor (the
-product path a dump-dir load takes). The oracle's operand-rounding emulation of the pass policy predicts 1.17e-3 / 9.0e-4 on
-these two cases, dominated by the single-pass fp16 q / k / P / V operands of the fused attention (8.5e-4 alone): this stress
-case is held to 2e-3 and REPORTED; the 1e-3 north-star bar is asserted on the synthetic weights everywhere else. DESIGN.md
-"precision" states the limitation."""
+product path a dump-dir load takes).
+
+With single fp16 q / k operands in the fused attention, the oracle's operand-rounding emulation of the pass policy predicts
+1.17e-3 / 9.0e-4 on these two cases (the attention operands alone inject 8.5e-4): that finding is why the attention of the 3-pass
+levels now takes q / k as fp16 hi + lo pairs (3-term split QK^T). Measured with it: 7.9e-4 / 6.4e-4 rel L2 at the default policy,
+3.7e-4 / 2.7e-4 with precision = 3 - inside the 1e-3 north-star bar, which this test asserts. DESIGN.md "precision" has the table.
+"""
 import os
 
 import numpy as np
@@ -39,8 +42,8 @@ def test_unet_realistic_statistics(ctx):
             res[prec] = (a, b)
             print(f"realistic-statistics weights, precision option {prec}: n=2 32x32 rel L2 {a[0]:.3e} max {a[1]:.3e}; "
                   f"n=1 64x64 L=77 rel L2 {b[0]:.3e} max {b[1]:.3e}")
-        assert max(max(v) for pair in res[0] for v in [pair]) < 2e-3
-        assert max(max(v) for pair in res[3] for v in [pair]) < 2e-3
+        assert max(max(v) for pair in res[0] for v in [pair]) < 1e-3
+        assert max(max(v) for pair in res[3] for v in [pair]) < 6e-4
     finally:
         ctx.set_option("precision", 0)
         ctx.init_synthetic(0)
