@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "attention.cuh"
 #include "kernels.cuh"
 #include "model.cuh"
 #include "runtime.cuh"
@@ -416,6 +417,10 @@ int sdb_set_option(sdb_ctx* ctx, const char* key, int value) {
     c.opt_splitk_chunk = value < 1 ? 1 : value;
   else if (k == "attn_split")
     c.opt_attn_split = value;
+  else if (k == "attn_regsplit")
+    g_attn_regsplit = value;
+  else if (k == "emb_hoist")
+    c.opt_emb_hoist = value;
   else if (k == "prefetch_w")
     c.opt_prefetch_w = value;
   else if (k == "mlp_passes")

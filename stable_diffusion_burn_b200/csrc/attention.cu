@@ -52,8 +52,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int DPAD, int NG, bool VMN, bool QK3>
-__global__ void __launch_bounds__(64 + 128 * NG, 1)
+// RS = true (register split, NG = 2 only): the block is padded to three full warpgroups — warps 0-3 = TMA producer, MMA issuer and
+// two idle warps, warps 4-11 = the two softmax groups — so that setmaxnreg can move registers between them: the first warpgroup
+// drops to 56 registers per thread, the softmax warpgroups rise to 224. With 10 warps ptxas budgets 65536 / 384 = 168 registers
+// per thread (allocation is per 4 warps) and the 128 score registers of a softmax thread left 12 values spilled to local memory,
+// ~20 reloads per key tile inside the exponentials loop (LDL in the SASS; ncu: long-scoreboard the top stall).
+template <int DPAD, int NG, bool VMN, bool QK3, bool RS>
+__global__ void __launch_bounds__((RS ? 128 : 64) + 128 * NG, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mq_lo,
                  const __grid_constant__ CUtensorMap mk_lo, const AttnParams p) {
@@ -78,6 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int SW0 = RS ? 4 : 2;  // first softmax warp
   pdl_trigger();
   const int q0 = blockIdx.x * (128 * NG);
   const int h = blockIdx.y;
@@ -118,6 +124,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   const int T = (kvlen + 127) / 128;
   // columns: S_g at g*128 ; O_g at NG*128 + g*DPAD
 
+  // (setmaxnreg sits INSIDE the role branches: ptxas budgets the code after a join with the smaller of the two limits)
+  if (warp < SW0) {
+  if (RS) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ======================================================================= TMA producer
     if (lane == 0) {
@@ -212,9 +221,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         __syncwarp();
       }
     }
+  }
   } else {
+    if (RS) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ======================================================================= softmax groups + epilogue
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - SW0) >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_sel = uint32_t(qd * 32) << 16;
@@ -338,14 +349,27 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   }
 }
 
-template <int DPAD, int NG, bool VMN, bool QK3>
-static void launch_attn2(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
+// option "attn_regsplit": NG = 2 launches use the register-split variant (see attention_kernel). Off by default: it removes every
+// spill (STACK 48 -> 0 bytes, no LDL / STL in the SASS) and is bit-identical, but measured neutral (143.38 ms per image with it,
+// 143.30 ms without, tools/step_time.py): the spill reloads were not what the softmax warps wait for.
+int g_attn_regsplit = 0;
+
+template <int DPAD, int NG, bool VMN, bool QK3, bool RS>
+static void launch_attn3(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
   constexpr int smem = AttnCfg<DPAD, NG, VMN, QK3>::SMEM;
   static DeviceOnce once;
   if (once.first())
-    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG, VMN, QK3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SDB_CUDA(cudaFuncSetAttribute(attention_kernel<DPAD, NG, VMN, QK3, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.Nq + 128 * NG - 1) / (128 * NG), p.heads, p.nb);
-  launch_k(attention_kernel<DPAD, NG, VMN, QK3>, grid, dim3(64 + 128 * NG), (size_t)smem, st, m.q, m.k, m.v, m.q_lo, m.k_lo, p);
+  launch_k(attention_kernel<DPAD, NG, VMN, QK3, RS>, grid, dim3((RS ? 128 : 64) + 128 * NG), (size_t)smem, st, m.q, m.k, m.v, m.q_lo,
+           m.k_lo, p);
+}
+template <int DPAD, int NG, bool VMN, bool QK3>
+static void launch_attn2(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {
+  if constexpr (NG == 2) {
+    if (g_attn_regsplit) return launch_attn3<DPAD, NG, VMN, QK3, true>(m, p, st);
+  }
+  launch_attn3<DPAD, NG, VMN, QK3, false>(m, p, st);
 }
 template <int DPAD, int NG>
 static void launch_attn(const AttnMaps& m, const AttnParams& p, cudaStream_t st) {

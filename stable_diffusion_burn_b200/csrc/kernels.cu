@@ -921,6 +921,87 @@ void time_embed_launch(const int* t, const float* w1, const float* b1, const flo
   SDB_CUDA(cudaGetLastError());
 }
 
+// Time embedding for ALL timesteps of a sampling schedule in one pass (the rows depend on t alone: sample_latent computes them once
+// per call instead of once per step; the weights of the 22 lin_embed layers, 103 MB of fp32, stream once per R rows instead of
+// once per step). Same arithmetic, in the same order, as gemv_kernel: the rows are bit-identical to the per-step path.
+//   y[row][N] = act(x[row][K] W[K][N] + b),  row = blockIdx.y * R + r
+// t_embed != null: x is the sinusoidal embedding of t_embed[row] (K = 320). t_rowmap != null: output row index = t_rowmap[row].
+template <int R>
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const float* __restrict__ x, const int* __restrict__ t_embed, const int* __restrict__ t_rowmap, int rows,
+                 const float* __restrict__ W, const float* __restrict__ b, int K, int N, int silu, float* __restrict__ y,
+                 long long y_stride) {
+  pdl_enter();
+  __shared__ float s_part[R][8][32];
+  __shared__ float s_x[R][1280];
+  const int r0 = blockIdx.y * R, nr = min(R, rows - r0);
+  for (int r = 0; r < nr; ++r) {
+    if (t_embed) {
+      const int t = t_embed[r0 + r];
+      for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+        const float f = expf((float)i * (float)(-9.210340371976184 / 160.0));
+        const float a = (float)t * f;
+        s_x[r][i] = cosf(a);
+        s_x[r][160 + i] = sinf(a);
+      }
+    } else {
+      for (int i = threadIdx.x; i < K; i += blockDim.x) s_x[r][i] = x[(size_t)(r0 + r) * K + i];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;
+  const int ks = threadIdx.x >> 5;  // 0..7
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (col < N)
+    for (int k = ks; k < K; k += 8) {
+      const float w = W[(size_t)k * N + col];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] += s_x[r][k] * w;  // rows >= nr read stale shared memory and are never stored
+    }
+#pragma unroll
+  for (int r = 0; r < R; ++r) s_part[r][ks][lane] = acc[r];
+  __syncthreads();
+  if (ks == 0 && col < N) {
+    for (int r = 0; r < nr; ++r) {
+      float s = b ? b[col] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += s_part[r][j][lane];
+      const long long orow = t_rowmap ? t_rowmap[r0 + r] : (r0 + r);
+      y[orow * y_stride + col] = silu ? silu_f(s) : s;
+    }
+  }
+}
+// rows of emb_all are indexed by the TIMESTEP VALUE (emb_all[t][N]): the in-graph selection needs no step counter
+void time_embed_rows_launch(const int* t_dev, int rows, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* w_all, const float* b_all, int n_all, float* hidden, float* emb_silu, float* emb_all,
+                            cudaStream_t st) {
+  constexpr int R = 5;
+  const dim3 gy(40, ceil_div(rows, R));
+  launch_k(gemv_rows_kernel<R>, gy, dim3(256), 0, st, (const float*)nullptr, t_dev, (const int*)nullptr, rows, w1, b1, 320, 1280, 1,
+           hidden, (long long)1280);
+  launch_k(gemv_rows_kernel<R>, gy, dim3(256), 0, st, (const float*)hidden, (const int*)nullptr, (const int*)nullptr, rows, w2, b2,
+           1280, 1280, 1, emb_silu, (long long)1280);
+  launch_k(gemv_rows_kernel<R>, dim3(ceil_div(n_all, 32), ceil_div(rows, R)), dim3(256), 0, st, (const float*)emb_silu,
+           (const int*)nullptr, t_dev, rows, w_all, b_all, 1280, n_all, 0, emb_all, (long long)n_all);
+  SDB_CUDA(cudaGetLastError());
+}
+// out[N] = emb_all[*t_dev][N]: the one launch of the UNet step graph that replaces the three GEMVs
+__global__ void __launch_bounds__(256)
+emb_select_kernel(const float* __restrict__ emb_all, const int* __restrict__ t_dev, int N, float* __restrict__ out) {
+  pdl_enter();
+  const float4* src = reinterpret_cast<const float4*>(emb_all + (size_t)(*t_dev) * N);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N / 4; i += gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(out)[i] = src[i];
+}
+void emb_select_launch(const float* emb_all, const int* t_dev, int N, float* out, cudaStream_t st) {
+  SDB_CHECK(N % 4 == 0, "emb_select: N must be a multiple of 4");
+  launch_k(emb_select_kernel, dim3(ceil_div(N / 4, 256)), dim3(256), 0, st, emb_all, t_dev, N, out);
+  SDB_CUDA(cudaGetLastError());
+}
+
 // ============================================================ CLIP token + position embedding
 // x[s][l][:] = E[tok[s][l]] + Pos[l] for l < L, zero rows up to Lp (reference clip/mod.rs:62-68)
 __global__ void embed_tokens_kernel(const int* __restrict__ tok, const float* __restrict__ E, const float* __restrict__ Pos,

@@ -78,6 +78,11 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
 // emb = lin2(silu(lin1([cos|sin](t*f)))) ; then for every ResBlock r: e_r = lin_embed_r(silu(emb))
 void time_embed_launch(const int* t_dev, const float* w1, const float* b1, const float* w2, const float* b2, float* hidden,
                        float* emb_silu, cudaStream_t st);
+// the same for `rows` timesteps at once (t_dev[rows]); emb_all[t][n_all] is indexed by the timestep value. Bit-identical rows.
+void time_embed_rows_launch(const int* t_dev, int rows, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* w_all, const float* b_all, int n_all, float* hidden, float* emb_silu, float* emb_all,
+                            cudaStream_t st);
+void emb_select_launch(const float* emb_all, const int* t_dev, int N, float* out, cudaStream_t st);
 // y[N] = x[K] @ W[K][N] + b  (tiny GEMV, W fp32 [in,out])
 void gemv_launch(const float* x, const float* W, const float* b, int K, int N, float* y, cudaStream_t st);
 

@@ -598,6 +598,7 @@ struct UNetIO {
   const int* t_dev;    // device scalar timestep
   float* out;          // [nb,4,H,W] NCHW
   int H, W;
+  const float* emb_all = nullptr;  // [1000][emb_total] rows precomputed per timestep value (sample_latent), or null
 };
 
 static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
@@ -610,14 +611,20 @@ static void unet_forward(Fwd& f, const UNetIO& io, const CtxState& cs) {
   float* emb_hidden = c.work.get<float>(1280);
   float* emb_silu = c.work.get<float>(1280);
   float* emb_rows = c.work.get<float>(m.emb_total);
-  {
-    KernelScope ks(c, KC_ELEMENTWISE);
-    time_embed_launch(io.t_dev, mptr(c, m.lin1_time.wi), m.lin1_time.bias, mptr(c, m.lin2_time.wi), m.lin2_time.bias,
-                      emb_hidden, emb_silu, c.stream);
-  }
-  {
-    KernelScope ks(c, KC_ELEMENTWISE, 2.0 * 1280 * m.emb_total, 4.0 * 1280 * m.emb_total);
-    gemv_launch(emb_silu, m.emb_w_all, m.emb_b_all, 1280, m.emb_total, emb_rows, c.stream);
+  if (io.emb_all) {
+    // the rows of this timestep were computed before the step loop (model_sample_dev): one copy instead of three GEMVs
+    KernelScope ks(c, KC_ELEMENTWISE, 0.0, 8.0 * m.emb_total);
+    emb_select_launch(io.emb_all, io.t_dev, m.emb_total, emb_rows, c.stream);
+  } else {
+    {
+      KernelScope ks(c, KC_ELEMENTWISE);
+      time_embed_launch(io.t_dev, mptr(c, m.lin1_time.wi), m.lin1_time.bias, mptr(c, m.lin2_time.wi), m.lin2_time.bias,
+                        emb_hidden, emb_silu, c.stream);
+    }
+    {
+      KernelScope ks(c, KC_ELEMENTWISE, 2.0 * 1280 * m.emb_total, 4.0 * 1280 * m.emb_total);
+      gemv_launch(emb_silu, m.emb_w_all, m.emb_b_all, 1280, m.emb_total, emb_rows, c.stream);
+    }
   }
   int st_index = 0;
   std::vector<Act> saved;
@@ -922,7 +929,7 @@ struct StreamJoin {  // run on c.stream ordered after / before the caller's stre
 
 // UNet pass over nb samples with per-sample context lengths. d_ctx_padded [nb][Lpad][768].
 static void unet_pass(Ctx& c, int nb, const float* d_x, const int* d_t, const float* d_ctx_padded, int Lpad, int* d_kvlen,
-                      int H, int W, float* d_out, const CtxState* shared_cs) {
+                      int H, int W, float* d_out, const CtxState* shared_cs, const float* emb_all = nullptr) {
   Fwd f(c, nb);
   const size_t mark = c.work.off;
   CtxState local;
@@ -932,6 +939,7 @@ static void unet_pass(Ctx& c, int nb, const float* d_x, const int* d_t, const fl
     cs = &local;
   }
   UNetIO io{d_x, d_t, d_out, H, W};
+  io.emb_all = emb_all;
   unet_forward(f, io, *cs);
   c.work.off = mark;
 }
@@ -1083,6 +1091,24 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
   SDB_CUDA(cudaMemcpyAsync(d_len, lens.data(), nb * 4, cudaMemcpyHostToDevice, c.stream));
   SDB_CUDA(cudaStreamSynchronize(c.stream));
 
+  // time-embedding rows of every timestep of the schedule, once per call (unet/mod.rs:19-30, 115-118, 718-722 depend on t alone).
+  // Fixed-size table indexed by the timestep value: the addresses of everything allocated after it do not depend on n_steps,
+  // which the cached step graphs rely on.
+  float* emb_all = nullptr;
+  if (c.opt_emb_hoist) {
+    emb_all = c.work.get<float>((size_t)1000 * m.emb_total);
+    const size_t mk = c.work.off;
+    float* hid = c.work.get<float>(ts.size() * 1280);
+    float* sil = c.work.get<float>(ts.size() * 1280);
+    {
+      KernelScope ks(c, KC_ELEMENTWISE, 2.0 * 1280 * m.emb_total * ts.size(), 4.0 * 1280 * m.emb_total * ((ts.size() + 4) / 5));
+      time_embed_rows_launch(d_t, (int)ts.size(), mptr(c, m.lin1_time.wi), m.lin1_time.bias, mptr(c, m.lin2_time.wi),
+                             m.lin2_time.bias, m.emb_w_all, m.emb_b_all, m.emb_total, hid, sil, emb_all, c.stream);
+    }
+    c.launches += 2;  // three launches under one scope
+    c.work.off = mk;  // stream order: the temporaries are dead before anything else is written there
+  }
+
   Fwd f(c, nb);
   CtxState cs;
   prepare_context(f, ctxp, Lpad, d_len, cs);  // context K/V: once per image, not once per step
@@ -1102,13 +1128,13 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
     if (!exec) {
       // warm-up pass outside capture (sets kernel attributes), then capture
       SDB_CUDA(cudaMemcpyAsync(d_tcur, d_t, 4, cudaMemcpyDeviceToDevice, c.stream));
-      unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs);
+      unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs, emb_all);
       SDB_CUDA(cudaStreamSynchronize(c.stream));
       const int64_t before = c.launches;
       cudaGraph_t graph;
       SDB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
       try {
-        unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs);
+        unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs, emb_all);
       } catch (...) {
         cudaGraph_t g2;
         cudaStreamEndCapture(c.stream, &g2);
@@ -1137,7 +1163,7 @@ void model_sample_dev(Ctx& c, const float* d_context, int n, int L, const float*
       c.launches += graph_launches;
     } else {
       c.work.off = work_mark;
-      unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs);
+      unet_pass(c, nb, xb, d_tcur, nullptr, Lpad, d_len, H, W, eps, &cs, emb_all);
     }
     KernelScope ks(c, KC_ELEMENTWISE);
     cfg_ddim_launch(eps, eps + le, xb, (long long)le, (float)scale, (float)std::sqrt(1.0 - a_t), (float)std::sqrt(a_t),

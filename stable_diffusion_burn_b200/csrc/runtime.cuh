@@ -131,7 +131,9 @@ struct Ctx {
   int opt_raw16 = 1;      // epilogues also write the fp16 hi/lo copy a later raw-operand consumer needs (no staging launch)
   int opt_mlp_passes = 0;   // 0: the transformer MLP (GEGLU + ff) follows its level's pass policy; 1: single fp16 pass everywhere
   int opt_attn_split = 1;   // fused attention on the 3-pass levels takes q / k as fp16 hi + lo pairs (fp32-class logits)
-  int opt_prefetch_w = 1;   // weight-bound GEMMs (<= 4 M tiles) prefetch their weight strip into L2 ahead of griddepcontrol.wait
+  int opt_emb_hoist = 1;    // sample_latent computes the time-embedding rows of every timestep once per call (not once per step)
+  int opt_prefetch_w = 0;   // 1: weight-bound GEMMs (<= 4 M tiles) prefetch their weight strip into L2 ahead of griddepcontrol.wait.
+                            // Measured off (tools/step_time.py, same process): 143.38 ms per image with it, 142.59 ms without
   int opt_gn_epilogue = 1;  // GroupNorm statistics produced by the GEMM epilogue that writes the tensor (no stats pass, no rendezvous)
   int opt_cluster = 1;    // CTA pairs issue cta_group::2 MMAs (256 x BN) wherever the M-tile count is even and K is not split
   // profiling

@@ -62,6 +62,27 @@ def test_attention(ctx, n, Nq, Nk, C, heads):
             ctx.set_option("attn_split", 1)
 
 
+def test_attention_register_split_bit_identical(ctx):
+    """option attn_regsplit = 1: the two-query-tile launches run a register-split variant (setmaxnreg moves registers from the
+    TMA / MMA warpgroup to the softmax warpgroups: no spills; measured neutral, so off by default). Same arithmetic in the same
+    order -> bit-identical to the 10-warp variant."""
+    rng = np.random.default_rng(11)
+    for n, Nq, Nk, C, heads in [(1, 4096, 4096, 320, 8), (2, 1024, 1024, 640, 8), (2, 256, 77, 320, 8), (1, 200, 300, 640, 8)]:
+        q = rng.standard_normal((n, Nq, C)).astype(np.float32)
+        k = rng.standard_normal((n, Nk, C)).astype(np.float32)
+        v = rng.standard_normal((n, Nk, C)).astype(np.float32)
+        for split in (1, 0):  # split q / k operands (<48,2,QK3>) and the single-operand kernels (<48,2>, <80,2>)
+            ctx.set_option("attn_split", split)
+            try:
+                a = ctx.test_attention(q, k, v, heads)
+                ctx.set_option("attn_regsplit", 1)
+                b = ctx.test_attention(q, k, v, heads)
+            finally:
+                ctx.set_option("attn_regsplit", 0)
+                ctx.set_option("attn_split", 1)
+            assert np.isfinite(a).all() and np.array_equal(a, b), (n, Nq, Nk, C, split)
+
+
 # ------------------------------------------------------------------ UNet::forward
 @pytest.mark.parametrize("case,x,t,c", [
     ("kat_zeros", lambda: np.zeros((1, 4, 64, 64), np.float32), 1, lambda: synth.kat_context()),
@@ -189,6 +210,21 @@ def test_batch_invariance(sd):
         # (tensor-core accumulation error ~1.2e-9*K, tools/diag_split.py); downstream fp16 operand roundings then
         # decorrelate, so two batch shapes differ by about one rounding-noise amplitude — each stays within 1e-3 of the oracle.
         assert e < 1e-3
+
+
+def test_time_embedding_hoist_bit_identical(sd):
+    """sample_latent computes the time-embedding rows of all timesteps once per call (gemv_rows_kernel) instead of three GEMVs
+    inside every step; the rows - and therefore the latents - are bit-identical to the per-step path (emb_hoist = 0), for a
+    schedule whose length is not a multiple of the 5 rows a CTA handles, and again on a second call with another schedule."""
+    c = synth.make_context(1, 9, seed=3); unc = synth.make_context(1, 2, seed=99)[0]; init = synth.make_latent(1, 32, 32, seed=8)
+    for steps in (7, 3):
+        new = sd.sample_latent(c, unc, 7.5, steps, init_latent=init, H=32, W=32)
+        sd.set_option("emb_hoist", 0)
+        try:
+            old = sd.sample_latent(c, unc, 7.5, steps, init_latent=init, H=32, W=32)
+        finally:
+            sd.set_option("emb_hoist", 1)
+        assert np.isfinite(new).all() and np.array_equal(new, old), steps
 
 
 def test_decode_batch8(sd):
