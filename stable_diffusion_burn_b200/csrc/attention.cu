@@ -38,12 +38,15 @@ struct AttnCfg {
   static constexpr int V_TX = VMN ? DC * 128 * 128 : 2 * DPAD * 128;    // bytes one V stage receives
   static constexpr int P_TILE = 2 * 128 * 128;                          // [128 rows][128 keys] fp16
   static constexpr int FIXED = NG * (Q_TILE + P_TILE) + 512 + 1024;
-  static constexpr int ST = (FIXED + 2 * (K_BYTES + V_BYTES) <= 225 * 1024) ? 2 : 1;  // K/V pipeline stages
+  // K/V pipeline stages: two when they fit beside the 1 KB of static shared memory (227 KB per CTA = 226 KB dynamic). The split-q/k
+  // d = 40 pair-of-query-tiles variant needs 225.5 KB for two: with ONE stage the MMA warp waited ~690 clk per key tile for K(j+1)
+  // (clock64 timeline, profiles/r2_attention_timeline_before.log)
+  static constexpr int ST = (FIXED + 2 * (K_BYTES + V_BYTES) <= 226 * 1024) ? 2 : 1;
   static constexpr int SMEM = FIXED + ST * (K_BYTES + V_BYTES);
   static constexpr int TMEM_NEED = NG * (128 + DPAD);
   static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
-  static_assert(SMEM <= 227 * 1024, "smem budget");
+  static_assert(SMEM <= 226 * 1024, "smem budget");
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -84,6 +87,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int SW0 = RS ? 4 : 2;  // first softmax warp
+  long long* const dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  constexpr int DJ0 = 8;  // stamped key tiles: DJ0 .. DJ0+3
+  if (dbg && threadIdx.x == 0) dbg[255] = clock64();
   pdl_trigger();
   const int q0 = blockIdx.x * (128 * NG);
   const int h = blockIdx.y;
@@ -129,7 +135,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
   if (RS) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ======================================================================= TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, NG * Cfg::Q_TILE);
 #pragma unroll
       for (int g = 0; g < NG; ++g)
@@ -173,12 +179,17 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     // ======================================================================= MMA issuer
     constexpr uint32_t idesc_s = make_idesc_f16(128, 128);
     constexpr uint32_t idesc_o = make_idesc_f16(128, DPAD, false, /*b_mn_major=*/VMN);
+    auto mstamp = [&](int j, int g, int k) {
+      if (dbg && lane == 0 && j >= DJ0 && j < DJ0 + 4) dbg[128 + (j - DJ0) * 16 + g * 8 + k] = clock64();
+    };
     auto issue_qk = [&](int g, int j) {
       const int st = j % ST;
+      mstamp(j - 1, g, 0);
       if (g == 0) mbar_wait(&k_full[st], (j / ST) & 1);
+      mstamp(j - 1, g, 4);
       if (j > 0) mbar_wait(&s_free[g], (j - 1) & 1);  // group g has copied S_g(j-1) out of TMEM
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t qa = smem_u32(sQ + g * Cfg::Q_TILE), ka = smem_u32(sK + st * Cfg::K_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DPAD / 16; ++kk) {
@@ -193,6 +204,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         umma_commit(&s_full[g]);
       }
       __syncwarp();
+      mstamp(j - 1, g, 1);
     };
     mbar_wait(q_full, 0);
     for (int g = 0; g < NG; ++g) issue_qk(g, 0);
@@ -203,9 +215,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // still in its exponentials and the next softmax never waits for the tensor pipe
         if (j + 1 < T) issue_qk(g, j + 1);
         if (g == 0) mbar_wait(&v_full[st], (j / ST) & 1);
+        mstamp(j, g, 5);
         mbar_wait(&p_full[g], j & 1);
+        mstamp(j, g, 2);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t pa = smem_u32(sP + g * Cfg::P_TILE), va = smem_u32(sV + st * Cfg::V_BYTES);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -219,6 +233,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           umma_commit(&pv_done[g]);
         }
         __syncwarp();
+        mstamp(j, g, 3);
       }
     }
   }
@@ -234,8 +249,13 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     uint8_t* prow = sP + g * Cfg::P_TILE + r * 128;
     const float sl2 = p.scale * 1.4426950408889634f;  // d^-1/2 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
+    auto sstamp = [&](int j, int k) {
+      if (dbg && qd == 0 && lane == 0 && j >= DJ0 && j < DJ0 + 4) dbg[g * 64 + (j - DJ0) * 8 + k] = clock64();
+    };
     for (int j = 0; j < T; ++j) {
+      sstamp(j, 0);
       mbar_wait(&s_full[g], j & 1);
+      sstamp(j, 1);
       tc_fence_after();
       uint32_t sv[128];
 #pragma unroll
@@ -243,6 +263,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[g]);
+      sstamp(j, 2);
       int valid = min(128, kvlen - j * 128);
       if (p.causal) valid = max(1, min(valid, q0 + g * 128 + r - j * 128 + 1));  // additive -inf mask above the diagonal
       // 8 independent max chains (a single chain of 128 dependent FMNMX would cost ~500 cycles of pure latency)
@@ -260,8 +281,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float m_new = fmaxf(m_run, mx * sl2);
       const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      sstamp(j, 3);
       if (j > 0) {
         mbar_wait(&pv_done[g], (j - 1) & 1);  // O_g holds PV(j-1); the P buffer is free again
+        sstamp(j, 4);
         tc_fence_after();
         if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
@@ -276,6 +299,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           tmem_st_wait();
         }
       }
+      sstamp(j, 5);
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums (ILP), folded in fixed order below
       const uint32_t prow_s = smem_u32(prow);
       auto emit = [&](auto masked) {
@@ -308,9 +332,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l_run = l_run * alpha + sum;
       m_run = m_new;
+      sstamp(j, 6);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&p_full[g]);
+      sstamp(j, 7);
     }
     // ---- epilogue: O / l -> fp16 hi(/lo)
     mbar_wait(&pv_done[g], (T - 1) & 1);

@@ -19,6 +19,7 @@ struct AttnParams {
   __half* out_hi;             // [nb*Nq][ldo], head h at columns h*d
   __half* out_lo;             // optional residual half
   int ldo;
+  long long* dbg;             // bring-up aid (SDB_ATTN_DBG): clock64 stamps of CTA (0,0,0), key tiles 8..11, or null
 };
 
 struct AttnMaps {

@@ -237,6 +237,22 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One elected lane of a converged warp (elect.sync). Single-thread regions that issue tcgen05.mma / TMA must be entered with this,
+// not with `lane == 0`: those instructions take their descriptors from UNIFORM registers, and in a branch ptxas cannot prove
+// single-threaded it wraps EVERY such instruction in an ELECT + BRA.U.ANY "waterfall" loop (~12 extra dependent instructions,
+// ~80 clk per MMA measured with clock64 stamps in the attention kernel); after elect.sync it emits them back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 (fp16/bf16 inputs, fp32 accumulate)
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

@@ -212,8 +212,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   //   MMA warp : consumes shared memory behind the mbarriers only: no wait
   //   epilogue : waits before its first read of residual / time-embedding rows; all of this kernel's stores follow that wait
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (one elected lane: see elect_one in common.cuh)
+    if (elect_one()) {
       // iteration -> (activation source, channel chunk, tap shift) and the weight map / K coordinate that go with it
       auto load_b = [&](int it, int s) {
         const CUtensorMap* bm = it < main_iters ? maps.b : maps.bx;
@@ -294,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (dbg && lane == 0 && it == it_begin) dbg[3] = clock64();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * L::BYTES);
         const uint32_t a_lo = a_hi + A_TILE_BYTES;
         const uint32_t b_hi = a_hi + L::A_TILES * A_TILE_BYTES;

@@ -209,8 +209,34 @@ void run_attention(Ctx& c, const AttnOp& a) {
              a.d, a.dpad, a.Nq, a.Nk, a.ldq, a.ldk, a.ldv, (const void*)a.kvlen);
     c.dbg_label = buf;
   }
-  KernelScope ks(c, KC_ATTN, flops, 0);
-  attention_launch(am, p, c.stream);
+  static const bool dbg_on = getenv("SDB_ATTN_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) SDB_CUDA(cudaMallocManaged(&dbg_buf, 256 * sizeof(long long)));
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+    memset(dbg_buf, 0, 256 * sizeof(long long));
+    p.dbg = dbg_buf;
+  }
+  {
+    KernelScope ks(c, KC_ATTN, flops, 0);
+    attention_launch(am, p, c.stream);
+  }
+  if (dbg_on) {  // bring-up aid: per-key-tile timeline of CTA (0,0,0), cycles since kernel entry
+    SDB_CUDA(cudaStreamSynchronize(c.stream));
+    const long long t0 = dbg_buf[255];
+    auto rel = [&](int i) { return dbg_buf[i] ? dbg_buf[i] - t0 : -1; };
+    fprintf(stderr, "attn_dbg nb=%d d=%d Nq=%d Nk=%d qk3=%d\n", a.nb, a.d, a.Nq, a.Nk, p.qk3);
+    for (int jj = 0; jj < 4; ++jj) {
+      for (int g = 0; g < 2; ++g)
+        fprintf(stderr, "  j=%d softmax g%d: wait_s %lld s_ready %lld loaded %lld max %lld pv_ok %lld rescaled %lld exps %lld p_arrive %lld\n", 8 + jj, g,
+                rel(g * 64 + jj * 8 + 0), rel(g * 64 + jj * 8 + 1), rel(g * 64 + jj * 8 + 2), rel(g * 64 + jj * 8 + 3), rel(g * 64 + jj * 8 + 4),
+                rel(g * 64 + jj * 8 + 5), rel(g * 64 + jj * 8 + 6), rel(g * 64 + jj * 8 + 7));
+      for (int g = 0; g < 2; ++g)
+        fprintf(stderr, "  j=%d mma g%d: qk(j+1) begin %lld k_ok %lld issued %lld | pv: v_ok %lld p_ok %lld issued %lld\n", 8 + jj, g,
+                rel(128 + jj * 16 + g * 8 + 0), rel(128 + jj * 16 + g * 8 + 4), rel(128 + jj * 16 + g * 8 + 1), rel(128 + jj * 16 + g * 8 + 5),
+                rel(128 + jj * 16 + g * 8 + 2), rel(128 + jj * 16 + g * 8 + 3));
+    }
+  }
 }
 
 static int pow2_floor(int x) {
