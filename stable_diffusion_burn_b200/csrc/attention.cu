@@ -36,14 +36,21 @@ struct AttnCfg {
   static constexpr int V_CHUNK = VMN ? 128 * 128 : ((DPAD * 128 + 1023) / 1024) * 1024;   // VMN: [128 keys][64 ch]; else [DPAD rows][64 keys]
   static constexpr int V_BYTES = (VMN ? DC : 2) * V_CHUNK;
   static constexpr int V_TX = VMN ? DC * 128 * 128 : 2 * DPAD * 128;    // bytes one V stage receives
-  static constexpr int P_TILE = 2 * 128 * 128;                          // [128 rows][128 keys] fp16
+  // P (the exponentials, fp16) goes to the PV product either through a swizzled shared-memory tile or — when the tensor memory has
+  // room for 64 more columns per query tile — through TENSOR MEMORY as the A operand of tcgen05.mma: each softmax thread stores
+  // its own row (128 fp16 = 64 columns of its lane) with tcgen05.st, no swizzle, no generic->async proxy fence, and the P tile
+  // (32 KB written + 32 KB read per query tile and key tile) leaves shared memory, whose bandwidth bounded the d = 40 kernel
+  // (QK^T + PV operands + P + TMA = 344 KB per key tile at 128 B/clk; profiles/r2_attention_timeline_after_elect_2stages.log)
+  static constexpr bool PT = NG * (128 + DPAD + 64) <= 512;
+  static constexpr int P_TILE = PT ? 0 : 2 * 128 * 128;                 // [128 rows][128 keys] fp16
   static constexpr int FIXED = NG * (Q_TILE + P_TILE) + 512 + 1024;
   // K/V pipeline stages: two when they fit beside the 1 KB of static shared memory (227 KB per CTA = 226 KB dynamic). The split-q/k
   // d = 40 pair-of-query-tiles variant needs 225.5 KB for two: with ONE stage the MMA warp waited ~690 clk per key tile for K(j+1)
   // (clock64 timeline, profiles/r2_attention_timeline_before.log)
   static constexpr int ST = (FIXED + 2 * (K_BYTES + V_BYTES) <= 226 * 1024) ? 2 : 1;
   static constexpr int SMEM = FIXED + ST * (K_BYTES + V_BYTES);
-  static constexpr int TMEM_NEED = NG * (128 + DPAD);
+  static constexpr int TMEM_NEED = NG * (128 + DPAD + (PT ? 64 : 0));
+  static constexpr int P_COL0 = NG * (128 + DPAD);                      // first P column (PT)
   static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM <= 226 * 1024, "smem budget");
@@ -227,7 +234,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             // K-major V^T: 16 keys = 32 bytes inside a 128-byte row; MN-major V: 16 keys = 16 rows of 128 bytes
             const uint32_t voff = VMN ? kk * 2048 : (kk / 4) * Cfg::V_CHUNK + (kk % 4) * 32;
             const uint64_t vdesc = VMN ? make_sdesc_sw128_mn(va + voff, Cfg::V_CHUNK) : make_sdesc_sw128(va + voff);
-            umma_f16(tmem_base + NG * 128 + g * DPAD, make_sdesc_sw128(pa + poff), vdesc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            if (Cfg::PT)  // A = P in tensor memory: 16 keys = 8 columns
+              umma_f16_ts(tmem_base + NG * 128 + g * DPAD, tmem_base + Cfg::P_COL0 + g * 64 + kk * 8, vdesc, idesc_o,
+                          (j > 0 || kk > 0) ? 1u : 0u);
+            else
+              umma_f16(tmem_base + NG * 128 + g * DPAD, make_sdesc_sw128(pa + poff), vdesc, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
           }
           if (g == NG - 1) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[g]);
@@ -247,6 +258,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     const uint32_t tS = tmem_base + g * 128 + lane_sel;
     const uint32_t tO = tmem_base + NG * 128 + g * DPAD + lane_sel;
     uint8_t* prow = sP + g * Cfg::P_TILE + r * 128;
+    const uint32_t tP = tmem_base + Cfg::P_COL0 + g * 64 + lane_sel;  // this row's 64 P columns (PT)
     const float sl2 = p.scale * 1.4426950408889634f;  // d^-1/2 * log2(e)
     float m_run = -INFINITY, l_run = 0.f;
     auto sstamp = [&](int j, int k) {
@@ -303,6 +315,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial row sums (ILP), folded in fixed order below
       const uint32_t prow_s = smem_u32(prow);
       auto emit = [&](auto masked) {
+        uint32_t pw[16];  // PT: 32 keys of this row, stored to tensor memory every fourth unit
+        (void)pw;
 #pragma unroll
         for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
           uint32_t w[4];
@@ -319,10 +333,16 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             const __half2 hp = __floats2half2_rn(p0, p1);
             w[e] = *reinterpret_cast<const uint32_t*>(&hp);
           }
-          const int chunk = u >> 3, uu = u & 7;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + chunk * 16384 + ((uu ^ (r & 7)) << 4)),
-                       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                       : "memory");
+          if (Cfg::PT) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pw[(u & 3) * 4 + e] = w[e];
+            if ((u & 3) == 3) tmem_st16(tP + (u >> 2) * 16, pw);
+          } else {
+            const int chunk = u >> 3, uu = u & 7;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_s + chunk * 16384 + ((uu ^ (r & 7)) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
         }
       };
       if (valid == 128)
@@ -333,7 +353,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
       l_run = l_run * alpha + sum;
       m_run = m_new;
       sstamp(j, 6);
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      if (Cfg::PT)
+        tmem_st_wait();       // this thread's P columns are in tensor memory
+      else
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(&p_full[g]);
       sstamp(j, 7);
