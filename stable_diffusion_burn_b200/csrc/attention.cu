@@ -291,14 +291,21 @@ attention_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
           if (i < valid) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(sv[i]));
       }
       const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])), fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-      const float m_new = fmaxf(m_run, mx * sl2);
-      const float alpha = ex2(m_run - m_new);  // 0 on the first tile (m_run = -inf)
+      // Lazy rescale with a threshold: the running maximum is only a reference point (softmax is shift invariant), so it is moved —
+      // and O_g / l rescaled — only when a row's maximum grew by more than 2^8; otherwise the tile is exponentiated against the
+      // stale reference and P may reach 256 (exact in fp16, fp32 sums). With a plain `m_new > m_run` test one of the 32 rows of
+      // a warp has a new maximum in ~97 % of the key tiles, i.e. the "lazy" rescale ran (3 x tcgen05.ld/st of O, ~340 clk) on
+      // almost every tile (clock64 timeline, profiles/r2_attention_timeline_p_in_tmem.log).
+      const float m_cand = fmaxf(m_run, mx * sl2);
+      const bool resc = __any_sync(0xffffffffu, m_cand > m_run + 8.0f);  // first tile: m_run = -inf -> true
+      const float m_new = resc ? m_cand : m_run;
+      const float alpha = resc ? ex2(m_run - m_new) : 1.0f;  // 0 on the first tile
       sstamp(j, 3);
       if (j > 0) {
         mbar_wait(&pv_done[g], (j - 1) & 1);  // O_g holds PV(j-1); the P buffer is free again
         sstamp(j, 4);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new > m_run)) {
+        if (resc) {
 #pragma unroll
           for (int c = 0; c < DPAD; c += 16) {
             uint32_t o[16];
