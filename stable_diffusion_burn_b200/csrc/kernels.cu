@@ -754,17 +754,23 @@ void conv3x3_cin4_launch(const float* x_nchw, int n, int H, int W, const float* 
 // TH = rows of the CTA tile (threads = 32 * TH): 8 for large images; 2 for small ones, where an 8-row tile would leave most SMs
 // idle (UNet conv_out at 64x64, batch 2: 32 CTAs with TH = 8 -> 140 us). With so few warps per SM nothing hides the latency of a
 // chunk's loads, so the small variant takes 64 channels per round (5 rounds for 320 channels instead of 20).
-template <int COUT, int TH, int CK>
-__global__ void __launch_bounds__(32 * TH)
+// KS = channel-split groups inside the CTA (threads = 32 * TH * KS): group ks takes the channel chunks ks, ks + KS, ... with its own
+// halo tile and weight slice, and the groups' partial sums are added in group order at the end (deterministic). The small-image
+// variant uses it to put 10 warps on an SM instead of 2: at 64x64, batch 2 the 128 two-warp CTAs left every SM with two warps
+// and the kernel latency-bound at 136 us (ncu launch list, profiles/r2_launches_summary.md).
+template <int COUT, int TH, int CK, int KS = 1>
+__global__ void __launch_bounds__(32 * TH * KS)
 conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, const double* __restrict__ sums,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                           const float* __restrict__ wp, const float* __restrict__ b, float* __restrict__ y) {
   pdl_enter();
-  constexpr int TW = 32, HP = TH + 2, WP = TW + 2, NPIX = HP * WP;
+  constexpr int TW = 32, HP = TH + 2, WP = TW + 2, NPIX = HP * WP, GT = 32 * TH;  // GT = threads of one group
+  constexpr int GROUP_F4 = (CK / 4) * NPIX + 9 * COUT * (CK / 4);                  // float4s of one group's tile + weights
   extern __shared__ float sm[];
   float* s_scale = sm;                           // [C]
   float* s_shift = sm + C;                       // [C]
-  float4* s_act = reinterpret_cast<float4*>(sm + 2 * C);   // [CK/4][NPIX] float4
+  const int ks = threadIdx.x / GT, gtid = threadIdx.x - ks * GT;
+  float4* s_act = reinterpret_cast<float4*>(sm + 2 * C) + (size_t)ks * GROUP_F4;   // [CK/4][NPIX] float4 (this group's)
   float4* s_w = s_act + (CK / 4) * NPIX;         // [9][COUT][CK/4] float4
   const int n = blockIdx.z;
   const int HW = H * W;
@@ -774,14 +780,14 @@ conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, cons
     const double inv_cnt = 1.0 / ((double)gs * HW);
     for (int c = threadIdx.x; c < C; c += blockDim.x) gn_affine(sums, n, c, gs, inv_cnt, eps, gamma, beta, s_scale[c], s_shift[c]);
   }
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = gtid & 31, ty = gtid >> 5;
   float acc[COUT];
 #pragma unroll
   for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-  for (int c0 = 0; c0 < C; c0 += CK) {
+  for (int c0 = ks * CK; c0 < C; c0 += CK * KS) {  // the launcher guarantees (C / CK) % KS == 0: every group runs the same rounds
     __syncthreads();  // the previous chunk's reads are done (and, first time round, the affine table is written)
     // halo tile: NPIX pixels x 4 channel quads
-    for (int i = threadIdx.x; i < NPIX * (CK / 4); i += blockDim.x) {
+    for (int i = gtid; i < NPIX * (CK / 4); i += GT) {
       const int pix = i / (CK / 4), q = i % (CK / 4);
       const int hh = h0 - 1 + pix / WP, ww = w0 - 1 + pix % WP;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -793,7 +799,7 @@ conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, cons
       }
       s_act[q * NPIX + pix] = v;  // zero outside the image == the conv's zero padding of the NORMALISED tensor
     }
-    for (int i = threadIdx.x; i < 9 * COUT * (CK / 4); i += blockDim.x) {
+    for (int i = gtid; i < 9 * COUT * (CK / 4); i += GT) {
       const int q = i % (CK / 4), o = (i / (CK / 4)) % COUT, tap = i / ((CK / 4) * COUT);
       s_w[i] = *reinterpret_cast<const float4*>(wp + ((size_t)o * 9 + tap) * C + c0 + q * 4);
     }
@@ -812,8 +818,24 @@ conv3x3_small_cout_kernel(const float* __restrict__ x, int H, int W, int C, cons
       }
     }
   }
+  if (KS > 1) {
+    // partial sums of the groups -> shared memory (over the tiles, which are dead now), added in group order by group 0
+    __syncthreads();
+    float* s_red = sm + 2 * C;  // [KS][COUT][GT]
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) s_red[(ks * COUT + o) * GT + gtid] = acc[o];
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        float a = s_red[o * GT + gtid];
+        for (int k = 1; k < KS; ++k) a += s_red[(k * COUT + o) * GT + gtid];
+        acc[o] = a;
+      }
+    }
+  }
   const int h = h0 + ty, w = w0 + tx;
-  if (h < H && w < W) {
+  if (ks == 0 && h < H && w < W) {
 #pragma unroll
     for (int o = 0; o < COUT; ++o) y[((size_t)n * COUT + o) * HW + (size_t)h * W + w] = acc[o] + b[o];
   }
@@ -822,18 +844,28 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
                                const float* beta, float eps, const float* w_packed, const float* b, int Cout,
                                float* y_nchw, cudaStream_t st) {
   SDB_CHECK(C % 16 == 0, "conv3x3_small_cout: channels must be a multiple of 16");
-  // too few 8-row tiles to fill the machine -> 2-row tiles, 64 channels per round
-  const bool small = (long long)ceil_div(W, 32) * ceil_div(H, 8) * n < 2 * 148 && C % 64 == 0;
-  const int th = small ? 2 : 8, ck = small ? 64 : 16;
-  dim3 grid(ceil_div(W, 32), ceil_div(H, th), n), block(32 * th);
-  auto smem = [&](int cout) { return (size_t)(2 * C + ck * (th + 2) * 34 + 9 * cout * ck) * sizeof(float); };
-#define SDB_SMALL_CONV(CO)                                                                                                          \
-  if (small) {                                                                                                                      \
+  // too few 8-row tiles to fill the machine -> 2-row tiles, 32 channels per round and group, the channel chunks split over
+  // KS = 5 or 4 groups of two warps (10 / 8 warps per CTA; 320 = 10 x 32 and 512 = 16 x 32 channels)
+  const bool small = (long long)ceil_div(W, 32) * ceil_div(H, 8) * n < 2 * 148 && C % 32 == 0;
+  const int ksplit = !small ? 1 : ((C / 32) % 5 == 0 ? 5 : ((C / 32) % 4 == 0 ? 4 : 1));
+  const int th = small ? 2 : 8, ck = small ? 32 : 16;
+  dim3 grid(ceil_div(W, 32), ceil_div(H, th), n), block(32 * th * ksplit);
+  auto smem = [&](int cout) {
+    return (size_t)(2 * C + std::max(ksplit * (ck * (th + 2) * 34 + 9 * cout * ck), ksplit * cout * 32 * th)) * sizeof(float);
+  };
+#define SDB_SMALL_KS(CO, KSV)                                                                                                       \
+  {                                                                                                                                 \
     static DeviceOnce once;                                                                                                         \
     if (once.first())                                                                                                               \
-      SDB_CUDA(cudaFuncSetAttribute(conv3x3_small_cout_kernel<CO, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-    launch_k(conv3x3_small_cout_kernel<CO, 2, 64>, grid, block, smem(CO), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b,      \
+      SDB_CUDA(cudaFuncSetAttribute(conv3x3_small_cout_kernel<CO, 2, 32, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                    160 * 1024));                                                                                   \
+    SDB_CHECK(smem(CO) <= 160 * 1024, "conv3x3_small_cout: shared memory");                                                         \
+    launch_k(conv3x3_small_cout_kernel<CO, 2, 32, KSV>, grid, block, smem(CO), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, \
              y_nchw);                                                                                                               \
+  }
+#define SDB_SMALL_CONV(CO)                                                                                                          \
+  if (small) {                                                                                                                      \
+    if (ksplit == 5) SDB_SMALL_KS(CO, 5) else if (ksplit == 4) SDB_SMALL_KS(CO, 4) else SDB_SMALL_KS(CO, 1)                          \
   } else                                                                                                                            \
     launch_k(conv3x3_small_cout_kernel<CO, 8, 16>, grid, block, smem(CO), st, x, H, W, C, sums, gamma, beta, eps, w_packed, b, y_nchw)
   if (Cout == 4) {
@@ -846,6 +878,7 @@ void conv3x3_small_cout_launch(const float* x, int n, int H, int W, int C, const
     throw Error("conv3x3_small_cout: Cout must be 3, 4 or 8");
   }
 #undef SDB_SMALL_CONV
+#undef SDB_SMALL_KS
   SDB_CUDA(cudaGetLastError());
 }
 
