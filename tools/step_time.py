@@ -1,5 +1,5 @@
 """A/B timing inside one process: 20-step sample_latent (graph replay) and decode, CUDA-event timed on the library's
-device entry points, for a list of option settings. Usage: python tools/step_time.py [key=v,key=v ...]"""
+device entry points, for a list of option settings. Usage: [BATCH=n REPS=7 ROUNDS=2] python tools/step_time.py [key=v,key=v ...]"""
 import ctypes as C
 import os
 import sys
@@ -43,13 +43,14 @@ def timeit(fn, reps):
     return ts[0], ts[len(ts) // 2]
 
 
-for rnd in range(2):
+REPS, ROUNDS = int(os.environ.get("REPS", 7)), int(os.environ.get("ROUNDS", 2))
+for rnd in range(ROUNDS):
     for v in variants:
         for k, val in v.items():
             c.set_option(k, int(val))
         for _ in range(2):
             sample(20)
-        t20 = timeit(lambda: sample(20), 7)
-        td = timeit(decode, 7)
+        t20 = timeit(lambda: sample(20), REPS)
+        td = timeit(decode, REPS)
         print(f"round {rnd} {v}: image min/med {t20[0]:.2f}/{t20[1]:.2f} ms; decode {td[0]:.2f}/{td[1]:.2f} ms; "
               f"unet step ~{(t20[0] - td[0]) / 20:.3f} ms", flush=True)
