@@ -37,9 +37,28 @@ def broadcast_weights(ctx, rank: int, world: int):
     which broadcasts the fp32 master arena + the per-norm eps table from rank 0 and is destroyed."""
     import torch
     import torch.distributed as dist
-    box = [ctx.nccl_unique_id() if rank == 0 else None]
+    uid = None
+    if rank == 0:
+        try:
+            uid = ctx.nccl_unique_id()
+        except Exception as e:  # libnccl.so.2 not loadable by the library: every rank takes the fallback below
+            import sys
+            print(f"[sdb200] library NCCL unavailable ({e}); broadcasting the weight arena through torch.distributed",
+                  file=sys.stderr, flush=True)
+    box = [uid]
     dist.broadcast_object_list(box, src=0, device=torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else None)
-    ctx.broadcast_weights(box[0], rank, world)
+    if box[0] is not None:
+        ctx.broadcast_weights(box[0], rank, world)
+        return
+    # fallback (the round-1 path): the same ONE broadcast of the fp32 master arena, issued through the existing process group.
+    # Carries tensors only: per-norm eps values of a dump-dir are not shipped (every rank must load the directory itself).
+    ptr, nbytes = ctx.weight_arena()
+
+    class _Arena:
+        __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+    arena = torch.as_tensor(_Arena(), device=torch.device("cuda", torch.cuda.current_device()))
+    dist.broadcast(arena, 0)
+    torch.cuda.synchronize()
 
 
 def gather_images(local_images: np.ndarray, n_images: int, rank: int, world: int):
